@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """Access to the committed outputs of the literal reference (tests/golden/make_golden.py)."""
+
+    def __init__(self):
+        self._z = np.load(GOLDEN, allow_pickle=False)
+
+    def case(self, name, device="cpu"):
+        out = {}
+        pre = name + "/"
+        for k in self._z.files:
+            if k.startswith(pre):
+                v = self._z[k]
+                if v.dtype.kind in "fiub" and v.dtype.kind != "U":
+                    t = torch.from_numpy(np.array(v))
+                    out[k[len(pre):]] = t.to(device) if t.ndim > 0 else t
+                else:
+                    out[k[len(pre):]] = v
+        return out
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()
+
+
+def rays_from(case, device="cpu"):
+    from oracle.mip360_oracle import Rays
+    return Rays(*[case[k].to(device) for k in Rays._fields])
