@@ -1,0 +1,210 @@
+/*
+ * mip360_b200.h — C ABI of the B200-native per-ray hot path of zhangkai0425/mipnerf360.
+ *
+ * The reference (/root/reference) is 100 % Python and defines no FFI; its hot path sits behind
+ * Python call signatures.  This header is the boundary a reference-side binding
+ * (ctypes) attaches to.  Each entry point names the reference function
+ * (file:line, relative to the reference root) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (sm_100a) unless the name ends in _host;
+ *   - tensors are dense row-major fp32 unless stated; "bf16" buffers are uint16_t bit patterns;
+ *   - B = rays, N = samples (intervals) per ray, S = B*N samples; t-vectors have N+1 knots;
+ *   - functions only enqueue work on `stream` (a cudaStream_t passed as void*); they never
+ *     allocate, never synchronise and never throw.  Return 0 on success or a negative
+ *     MIP360_ERR_* code; mip360_last_error() returns a static message for the calling thread;
+ *   - inputs are never modified (the reference mutates several of its inputs).
+ */
+#ifndef MIP360_B200_H
+#define MIP360_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIP360_OK 0
+#define MIP360_ERR_ARG (-1)         /* null pointer, bad size, unsupported N */
+#define MIP360_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define MIP360_ERR_UNSUPPORTED (-3) /* shape not supported by the tcgen05 path */
+
+#define MIP360_MAX_SAMPLES 128 /* N <= 128: one warp holds a ray (4 intervals per lane) */
+#define MIP360_ENC_DIM 42      /* 21 directions x {sin, cos}; intern/encoding.py:9-30 */
+#define MIP360_VDIR_DIM 16     /* 4 scales x {sin,cos} x {theta,phi}; intern/encoding.py:67 */
+#define MIP360_MLP_IN 58       /* model.py:39,127 */
+#define MIP360_MLP_IN_PAD 64   /* bf16 row of the MLP input: 58 features + 6 zero columns = 128 B */
+
+typedef void* mip360_stream_t;
+
+const char* mip360_last_error(void);
+int mip360_version(void);
+/* number of kernel launches issued through this library since load / since the last reset */
+long long mip360_launch_count(void);
+void mip360_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  level-0 sampling               intern/ray.py:100-111, intern/parameterization.py:15-21
+ *   t = g(s*g(far) + (1-s)*g(near)), g(x) = 1/(x+1e-6); s_lin[N+1] = linspace(0,1,N+1) is
+ *   supplied by the host binding so that it is the same fp32 vector the reference uses.
+ *   t_rand [B,N+1] (the torch.rand draw of ray.py:106) or NULL for the deterministic mode.
+ * ------------------------------------------------------------------------------------------ */
+int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand,
+                         float* t_out, int B, int N, mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  cast -> Gaussian -> contract -> IPE (+ view-direction encoding), fused
+ *     intern/parameterization.py:85-136 (conical_frustum_to_gaussian, gaussian_to_xyz,
+ *     gaussian_contract, contract, para_rays), intern/encoding.py:33-61 and :69-90,
+ *     model.py:85-88 / 173-176 (concatenation order).
+ *
+ *   mip360_frustum_norm_sq: pre-pass for the reference's batch-global contraction
+ *     (App. A1): *norm_sq += sum over all samples of |d * t_mean|^2.  *norm_sq must be
+ *     zeroed by the caller (so that several shards can be accumulated into one scalar).
+ *   t0/t1 are given as two pointers with a common row stride so that both t_vals[:, :-1] /
+ *     t_vals[:, 1:] views (stride N+1) and separate contiguous t0, t1 (stride N) work.
+ *   contract_mode: 0 = reference (global Frobenius norm, read from *norm_sq),
+ *                  1 = per-point contraction (paper), 2 = no contraction.
+ *   add_origins: 1 = means += origins after the contraction (para_rays, App. A2); 0 = not
+ *     (conical_frustum_to_gaussian itself).
+ *   Outputs, each may be NULL: means [S,3], covs [S,3,3], enc [S,42] (fp32, needs means/covs
+ *     semantics of the reference: IPE of the returned mean and cov), x_bf16 [S,64] = the MLP
+ *     input row: 42 IPE features, 16 view-direction features, 6 zeros, rounded to bf16.
+ * ------------------------------------------------------------------------------------------ */
+int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const float* directions, int B, int N,
+                           double* norm_sq, mip360_stream_t stream);
+int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
+                    const float* viewdirs, const float* radii, const double* norm_sq, int B, int N,
+                    int contract_mode, int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16,
+                    mip360_stream_t stream);
+
+/* stand-alone pieces of the same arithmetic, for the reference's unfused free functions */
+/* intern/parameterization.py:31-62 (diag=False): d [B,3], t_mean/t_var/r_var [B,N] */
+int mip360_gaussian_to_xyz(const float* directions, const float* t_mean, const float* t_var, const float* r_var,
+                           int B, int N, float* means, float* covs, mip360_stream_t stream);
+/* sum of squares of n floats accumulated into *out (double, caller-zeroed): torch.norm of parameterization.py:25 */
+int mip360_sum_sq(const float* x, long long n, double* out, mip360_stream_t stream);
+/* intern/parameterization.py:23-29: y = x if ||x||_F <= 1 else (2-1/n)(x/n), n^2 = *norm_sq */
+int mip360_contract(const float* x, long long n, const double* norm_sq, float* y, mip360_stream_t stream);
+/* intern/parameterization.py:64-83 on S samples; covs_in/out [S,3,3]; closed-form Jacobian (App. A2) */
+int mip360_gaussian_contract(const float* means_in, const float* covs_in, const double* norm_sq, long long S,
+                             float* means_out, float* covs_out, mip360_stream_t stream);
+/* intern/encoding.py:33-61: mean [S,3], cov [S,3,3] -> enc [S,42] */
+int mip360_ipe(const float* means, const float* covs, long long S, float* enc, mip360_stream_t stream);
+/* intern/encoding.py:69-90: viewdirs [B,3] -> enc [B,4*n_scales], scales 2^min_deg .. 2^(max_deg-1) */
+int mip360_viewdir_enc(const float* viewdirs, int B, int min_deg, int max_deg, float* enc, mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  hierarchical resampling         intern/ray.py:12-57 and :118-153
+ *   mip360_blur_weights:  ray.py:137-142 (max-pool 2, avg-pool 2, + resample_padding) -> [B,N]
+ *   mip360_resample_cdf:  ray.py:15-27   weights [B,N] -> cdf [B,N+1]
+ *   mip360_resample_invert: ray.py:41-56 bins [B,N+1], cdf [B,N+1], u [B,M] (u_row_stride 0 =
+ *     one shared row) -> samples [B,M] and, if idx != NULL, idx [B,M] = index of the last cdf knot
+ *     <= u ("bin index"; bit-exact vs. searchsorted(right)-1, App. B2).
+ *   mip360_resample: the whole no_grad block of ray.py:136-149 in one kernel.  u_base [M] is the
+ *     stratum vector (randomized: arange(M)*(1/M); deterministic: linspace(0,1-eps,M)), jitter
+ *     [B,M] the uniform_(0,1/M-eps) draw or NULL; randomized => u = min(u_base+u_base+jitter,1-eps)
+ *     (the doubling is the reference's, App. A5).  M must equal N+1 (ray.py:146).
+ * ------------------------------------------------------------------------------------------ */
+int mip360_blur_weights(const float* weights, int B, int N, float resample_padding, float* out,
+                        mip360_stream_t stream);
+int mip360_resample_cdf(const float* weights, int B, int N, float* cdf, mip360_stream_t stream);
+int mip360_resample_invert(const float* bins, const float* cdf, const float* u, int u_row_stride, int B, int N,
+                           int M, float* samples, int32_t* idx, mip360_stream_t stream);
+int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
+                    int B, int N, float resample_padding, int blur, float* new_t, mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  volume compositing              intern/ray.py:155-191, model.py:59-78, model.py:184-185
+ *   head_mode 0: rgb [B,N,3] and density [B,N] are final values (volumetric_rendering as is).
+ *   head_mode 1: raw [B,N,4] = (sigmoid density head, sigmoid colour head) straight from the MLP;
+ *     density = softplus(raw0 + density_bias), rgb = raw123*(1+2*rgb_padding) - rgb_padding.
+ *   weights-only variant (density_to_weight): density_mode 0 = density given, 1 = raw logits,
+ *     density = softplus(raw + density_bias) (model.py:92).
+ *   Backward: g_rgb [B,3], g_acc [B], g_w [B,N] (any may be NULL) -> gradient w.r.t. rgb/density
+ *     (head_mode 0: g_rgb_in [B,N,3], g_density [B,N]) or raw (head_mode 1: g_raw [B,N,4]; if
+ *     g_raw_bf16 != NULL the same values are also written as bf16 rows of 64 (cols 4..63 zero),
+ *     the A operand of the head dgrad/wgrad GEMMs).  distance carries no gradient.
+ * ------------------------------------------------------------------------------------------ */
+int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
+                         int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
+                         float* comp_rgb, float* distance, float* acc, float* weights, mip360_stream_t stream);
+int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
+                         int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
+                         const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in,
+                         float* g_density, float* g_raw, uint16_t* g_raw_bf16, mip360_stream_t stream);
+int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
+                                 int density_mode, float density_bias, float* weights, mip360_stream_t stream);
+int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
+                                 int density_mode, float density_bias, const float* g_w, float* g_density,
+                                 uint16_t* g_raw_bf16, mip360_stream_t stream);
+/* intern/parameterization.py:5-8 incl. the in-place eps shifts one call observes (App. A4):
+ * s = (1/(t+e) - 1/(near+e)) / (1/(far+e) - 1/(near+2e)); t_shift = t + e (may be NULL) */
+int mip360_t_to_s(const float* t_vals, const float* near, const float* far, int B, int K, float* s_vals,
+                  float* t_shift, mip360_stream_t stream);
+/* intern/parameterization.py:10-13 */
+int mip360_s_to_t(const float* s_vals, const float* near, const float* far, int B, int K, float* t_vals,
+                  mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  distortion regulariser          intern/regularization.py:3-19 (O(N) form, App. A9/B4)
+ *   loss = sum over rays; per_ray [B] optional; partials = workspace of >= mip360_partials_len(B)
+ *   doubles.  bwd: g_w [B,N] = g_loss * dloss/dw (g_loss read from device scalar g_loss_ptr).
+ * ------------------------------------------------------------------------------------------ */
+int mip360_partials_len(int B);
+int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int N, float* per_ray,
+                          double* partials, float* loss, mip360_stream_t stream);
+int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int N, const float* g_loss_ptr,
+                          float* g_w, mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  interlevel (proposal) loss      intern/distillation.py:4-51, intern/loss.py:6-21
+ *   mip360_bounds_per_ray: b[r,i] = sum_j w_fine[r,j] [t0_j <= R_i and t1_j >= L_i] (App. B5).
+ *   mip360_bounds_reduce: column sums over rays -> bound_total [N] (the value the reference
+ *     broadcasts to every ray, App. A6); accumulates into bound_total (caller-zeroed doubles) so
+ *     shards / ranks can be combined.
+ *   mip360_interlevel_fwd: loss = sum relu(bnd - w_hat)^2/(w_hat+1e-6) / batch_div.  bound_mode 0:
+ *     bnd = bound_total[i] (reference), 1: bnd = b[r,i] (per-ray, paper-style).
+ *   mip360_interlevel_bwd: g_w_hat = g_loss * d loss / d w_hat (bounds are detached).
+ * ------------------------------------------------------------------------------------------ */
+int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N,
+                          float* b_out, mip360_stream_t stream);
+int mip360_bounds_reduce(const float* b, int B, int N, double* bound_total, mip360_stream_t stream);
+int mip360_interlevel_fwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
+                          int bound_mode, float batch_div, double* partials, float* loss, mip360_stream_t stream);
+int mip360_interlevel_bwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
+                          int bound_mode, float batch_div, const float* g_loss_ptr, float* g_w_hat,
+                          mip360_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  MLP GEMMs on tcgen05 / TMEM / TMA      model.py:43-53, :91 (prop_net); :131-158, :179-181 (nerf_net)
+ *   All matrices bf16 row-major, fp32 accumulation in tensor memory.
+ *   mip360_linear_fwd:  Y[M,N] = act(X[M,K] * W[N,K]^T + bias[N]).
+ *       act: 0 none, 1 ReLU, 2 Sigmoid.  out_bf16 [M,N] and/or out_f32 [M,n_valid] (heads: only the
+ *       first n_valid columns are stored, fp32).  K % 64 == 0, N % 64 == 0, N <= 256 or N % 256 == 0.
+ *   mip360_linear_dgrad: dX[M,K] = (dY[M,N] * Wt[K,N]^T) .* act'(Yprev[M,K]) with Wt = W^T stored
+ *       [K,N] row-major, act' from the saved *output* of the previous layer (ReLU: y>0, Sigmoid: y(1-y)).
+ *   mip360_linear_wgrad: dW[N,K] (+)= dY[M,N]^T * X[M,K] (fp32, split over M with atomic adds, so dW
+ *       must be zeroed by the caller when accumulate == 0 is not used); db[N] += column sums of dY.
+ *   mip360_cast_weight: fp32 W[N,K] -> bf16 Wb[Npad,Kpad] (zero padded) and optionally Wt[Kpad,Npad].
+ * ------------------------------------------------------------------------------------------ */
+int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
+                      uint16_t* out_bf16, float* out_f32, int n_valid, mip360_stream_t stream);
+int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,
+                        uint16_t* dX, mip360_stream_t stream);
+int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int K, float* dW, float* db,
+                        mip360_stream_t stream);
+int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_t* Wb, uint16_t* Wt,
+                       mip360_stream_t stream);
+/* number of SMs the persistent GEMM grids are sized for (148 on B200) */
+int mip360_sm_count(void);
+
+/* fused AdamW over one flat fp32 parameter tensor (train.py:38,63,81 — "next" row f3 of SURVEY §8):
+ * decoupled weight decay, bias correction from `step` (1-based), optional bf16 re-cast of the weights */
+int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, mip360_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIP360_B200_H */

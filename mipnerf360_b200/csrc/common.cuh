@@ -1,0 +1,112 @@
+// Shared device/host helpers for the per-ray kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mip360_b200.h"
+
+#define FULL_MASK 0xffffffffu
+
+namespace mip360 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+#define MIP_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) {                              \
+      mip360::set_error(__VA_ARGS__);           \
+      return MIP360_ERR_ARG;                    \
+    }                                           \
+  } while (0)
+
+#define MIP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      mip360::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+      return MIP360_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define MIP_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    mip360::count_launch();                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess) {                                                             \
+      mip360::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return MIP360_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+// ---- warp primitives -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+// inclusive scan across the 32 lanes
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_up_sync(FULL_MASK, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+// inclusive suffix scan (sum over lanes >= lane)
+__device__ __forceinline__ float warp_scan_incl_rev(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float n = __shfl_down_sync(FULL_MASK, v, o);
+    if (lane + o < 32) v += n;
+  }
+  return v;
+}
+
+// Block-level sum of one double per thread into partials[blockIdx.x] (deterministic order).
+template <int THREADS>
+__device__ __forceinline__ void block_sum_to_partial(double v, double* partials) {
+  __shared__ double sm_part[THREADS / 32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm_part[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += sm_part[i];
+    partials[blockIdx.x] = s;
+  }
+}
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // torch.nn.Softplus(beta=1, threshold=20): x if x > 20 else log1p(exp(x))
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(uint32_t(b) << 16); }
+
+// torch.nan_to_num defaults: nan -> 0 (or given), +inf -> FLT_MAX, -inf -> -FLT_MAX
+__device__ __forceinline__ float nan_to_num_f(float x, float nan_val = 0.f) {
+  if (isnan(x)) return nan_val;
+  if (isinf(x)) return x > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+  return x;
+}
+
+constexpr float G_EPS = 1e-6f;  // intern/parameterization.py:19
+
+}  // namespace mip360

@@ -1,0 +1,343 @@
+// K3: volume compositing (intern/ray.py:155-191, model.py:59-78, model.py:184-185) forward and
+// backward, plus the t<->s maps of intern/parameterization.py:5-13.  One warp per ray: the ray's knots
+// and per-sample values are staged in shared memory with coalesced loads, each lane owns a contiguous
+// chunk of ceil(N/32) intervals, the transmittance is a warp exclusive scan.
+#include "common.cuh"
+
+namespace mip360 {
+
+constexpr int CP_WARPS = 4;
+constexpr int CP_MAXC = (MIP360_MAX_SAMPLES + 31) / 32;
+
+struct __align__(16) CompositeSmem {
+  float t[MIP360_MAX_SAMPLES + 1];
+  float sigma[MIP360_MAX_SAMPLES];       // density after activation
+  float aux[MIP360_MAX_SAMPLES];         // head_mode 1: post-sigmoid density head value y0
+  float rgb[MIP360_MAX_SAMPLES * 3];     // colour after padding
+  float gw[MIP360_MAX_SAMPLES];          // backward: total dL/dw
+};
+
+struct RayScan {
+  float dd[CP_MAXC], T[CP_MAXC], w[CP_MAXC], delta[CP_MAXC];
+};
+
+// weights of one ray: lane-chunked exclusive scan of sigma*delta
+__device__ __forceinline__ void ray_weights(const CompositeSmem& s, int N, int C, int j0, float dnorm, int lane,
+                                            RayScan& r) {
+  float run = 0.f;
+  float excl[CP_MAXC];
+#pragma unroll
+  for (int c = 0; c < CP_MAXC; ++c) {
+    const int j = j0 + c;
+    r.dd[c] = 0.f;
+    r.delta[c] = 0.f;
+    if (c < C && j < N) {
+      r.delta[c] = (s.t[j + 1] - s.t[j]) * dnorm;
+      r.dd[c] = s.sigma[j] * r.delta[c];
+    }
+    excl[c] = run;
+    run += r.dd[c];
+  }
+  const float off = warp_scan_incl(run, lane) - run;
+#pragma unroll
+  for (int c = 0; c < CP_MAXC; ++c) {
+    r.T[c] = expf(-(off + excl[c]));
+    const float alpha = 1.f - expf(-r.dd[c]);
+    r.w[c] = alpha * r.T[c];
+  }
+}
+
+// stage one ray.  mode_full: rgb too.  head_mode 1: raw [N,4] post-sigmoid head outputs.
+__device__ __forceinline__ void stage_ray(CompositeSmem& s, const float* rgb_or_raw, const float* density,
+                                          const float* t_vals, long long b, int N, int head_mode, bool with_rgb,
+                                          int density_mode, float density_bias, float rgb_padding, int lane) {
+  const float* trow = t_vals + b * (N + 1);
+  for (int k = lane; k <= N; k += 32) s.t[k] = trow[k];
+  if (head_mode == 1) {
+    const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + b * N;
+    const float scale = 1.f + 2.f * rgb_padding;
+    for (int j = lane; j < N; j += 32) {
+      const float4 v = raw4[j];
+      s.aux[j] = v.x;
+      s.sigma[j] = softplus_f(v.x + density_bias);
+      s.rgb[j * 3 + 0] = v.y * scale - rgb_padding;
+      s.rgb[j * 3 + 1] = v.z * scale - rgb_padding;
+      s.rgb[j * 3 + 2] = v.w * scale - rgb_padding;
+    }
+  } else {
+    const float* drow = density + b * N;
+    for (int j = lane; j < N; j += 32) {
+      const float v = drow[j];
+      s.aux[j] = v;
+      s.sigma[j] = density_mode == 1 ? softplus_f(v + density_bias) : v;
+    }
+    if (with_rgb) {
+      const float* crow = rgb_or_raw + b * N * 3;
+      for (int e = lane; e < N * 3; e += 32) s.rgb[e] = crow[e];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CP_WARPS * 32)
+composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
+                     const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
+                     int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                     float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
+                     float* __restrict__ weights) {
+  __shared__ CompositeSmem sm[CP_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CompositeSmem& s = sm[warp];
+  const int C = (N + 31) >> 5, j0 = lane * C;
+  for (int b = blockIdx.x * CP_WARPS + warp; b < B; b += gridDim.x * CP_WARPS) {
+    stage_ray(s, rgb_or_raw, density, t_vals, b, N, head_mode, !weights_only, density_mode, density_bias, rgb_padding,
+              lane);
+    const float dx = dirs[b * 3], dy = dirs[b * 3 + 1], dz = dirs[b * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    __syncwarp();
+    RayScan r;
+    ray_weights(s, N, C, j0, dnorm, lane, r);
+    float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP_MAXC; ++c) {
+      const int j = j0 + c;
+      if (c < C && j < N) {
+        if (weights) weights[(long long)b * N + j] = r.w[c];
+        a += r.w[c];
+        if (!weights_only) {
+          cr += r.w[c] * s.rgb[j * 3 + 0];
+          cg += r.w[c] * s.rgb[j * 3 + 1];
+          cb += r.w[c] * s.rgb[j * 3 + 2];
+          wt += r.w[c] * (0.5f * (s.t[j] + s.t[j + 1]));
+        }
+      }
+    }
+    if (!weights_only) {
+      a = warp_sum(a); cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); wt = warp_sum(wt);
+      if (lane == 0) {
+        float dist = nan_to_num_f(wt / a);
+        dist = fminf(fmaxf(dist, s.t[0]), s.t[N]);
+        if (white_bkgd) {
+          const float bg = 1.f - a;
+          cr += bg; cg += bg; cb += bg;
+        }
+        comp_rgb[b * 3 + 0] = cr;
+        comp_rgb[b * 3 + 1] = cg;
+        comp_rgb[b * 3 + 2] = cb;
+        distance[b] = dist;
+        acc_out[b] = a;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Backward.  G_j = g_w_j + g_rgb . c_j + g_acc' is the total gradient reaching w_j;
+//   dL/d(dd_j) = G_j T_j e^{-dd_j} - sum_{k>j} G_k w_k ,  dL/dsigma_j = dL/d(dd_j) delta_j.
+__global__ void __launch_bounds__(CP_WARPS * 32)
+composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
+                     const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
+                     int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                     const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
+                     float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw,
+                     uint16_t* __restrict__ g_raw_bf16) {
+  __shared__ CompositeSmem sm[CP_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CompositeSmem& s = sm[warp];
+  const int C = (N + 31) >> 5, j0 = lane * C;
+  const float cscale = 1.f + 2.f * rgb_padding;
+  for (int b = blockIdx.x * CP_WARPS + warp; b < B; b += gridDim.x * CP_WARPS) {
+    stage_ray(s, rgb_or_raw, density, t_vals, b, N, head_mode, !weights_only, density_mode, density_bias, rgb_padding,
+              lane);
+    if (g_w) {
+      for (int j = lane; j < N; j += 32) s.gw[j] = g_w[(long long)b * N + j];
+    }
+    const float dx = dirs[b * 3], dy = dirs[b * 3 + 1], dz = dirs[b * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+    if (!weights_only) {
+      if (g_rgb) { gr = g_rgb[b * 3]; gg = g_rgb[b * 3 + 1]; gb = g_rgb[b * 3 + 2]; }
+      if (g_acc) ga = g_acc[b];
+      if (white_bkgd) ga -= (gr + gg + gb);
+    }
+    __syncwarp();
+    RayScan r;
+    ray_weights(s, N, C, j0, dnorm, lane, r);
+    float G[CP_MAXC], run = 0.f, excl_rev[CP_MAXC];
+    // suffix sums of G_k w_k: walk the lane's chunk backwards
+#pragma unroll
+    for (int c = CP_MAXC - 1; c >= 0; --c) {
+      const int j = j0 + c;
+      G[c] = 0.f;
+      if (c < C && j < N) {
+        G[c] = (g_w ? s.gw[j] : 0.f) + ga;
+        if (!weights_only) G[c] += gr * s.rgb[j * 3] + gg * s.rgb[j * 3 + 1] + gb * s.rgb[j * 3 + 2];
+      }
+      excl_rev[c] = run;
+      run += G[c] * r.w[c];
+    }
+    const float off = warp_scan_incl_rev(run, lane) - run;
+#pragma unroll
+    for (int c = 0; c < CP_MAXC; ++c) {
+      const int j = j0 + c;
+      if (c < C && j < N) {
+        const float g_dd = G[c] * r.T[c] * expf(-r.dd[c]) - (off + excl_rev[c]);
+        const float g_sigma = g_dd * r.delta[c];
+        const long long e = (long long)b * N + j;
+        if (head_mode == 1) {
+          const float y0 = s.aux[j];
+          // sigma = softplus(y0 + bias): d/dy0 = sigmoid(y0 + bias); colour = y*(1+2p) - p
+          const float g_y0 = g_sigma * sigmoid_f(y0 + density_bias);
+          const float g_y1 = r.w[c] * gr * cscale, g_y2 = r.w[c] * gg * cscale, g_y3 = r.w[c] * gb * cscale;
+          if (g_raw) reinterpret_cast<float4*>(g_raw)[e] = make_float4(g_y0, g_y1, g_y2, g_y3);
+          if (g_raw_bf16) {
+            // gradient w.r.t. the head pre-activations (both heads end in a Sigmoid, model.py:150-158):
+            // recover the post-sigmoid colour values from the padded colour
+            const float y1 = (s.rgb[j * 3 + 0] + rgb_padding) / cscale;
+            const float y2 = (s.rgb[j * 3 + 1] + rgb_padding) / cscale;
+            const float y3 = (s.rgb[j * 3 + 2] + rgb_padding) / cscale;
+            uint4* row = reinterpret_cast<uint4*>(g_raw_bf16 + e * 64);
+            row[0] = make_uint4(pack_bf16x2(g_y0 * y0 * (1.f - y0), g_y1 * y1 * (1.f - y1)),
+                                pack_bf16x2(g_y2 * y2 * (1.f - y2), g_y3 * y3 * (1.f - y3)), 0u, 0u);
+#pragma unroll
+            for (int q = 1; q < 8; ++q) row[q] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+          if (density_mode == 1) {
+            const float g_z = g_sigma * sigmoid_f(s.aux[j] + density_bias);
+            if (g_density) g_density[e] = g_z;
+            if (g_raw_bf16) {
+              uint4* row = reinterpret_cast<uint4*>(g_raw_bf16 + e * 64);
+              row[0] = make_uint4(pack_bf16x2(g_z, 0.f), 0u, 0u, 0u);
+#pragma unroll
+              for (int q = 1; q < 8; ++q) row[q] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          } else if (g_density) {
+            g_density[e] = g_sigma;
+          }
+          if (!weights_only && g_rgb_in) {
+            g_rgb_in[e * 3 + 0] = r.w[c] * gr;
+            g_rgb_in[e * 3 + 1] = r.w[c] * gg;
+            g_rgb_in[e * 3 + 2] = r.w[c] * gb;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// intern/parameterization.py:5-8 with the eps shifts a single reference call observes (App. A4)
+__global__ void __launch_bounds__(256)
+t_to_s_kernel(const float* __restrict__ t_vals, const float* __restrict__ near, const float* __restrict__ far, int B,
+              int K, float* __restrict__ s_vals, float* __restrict__ t_shift) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)B * K) return;
+  const int b = (int)(e / K);
+  const float t1 = t_vals[e] + G_EPS;
+  const float n1 = near[b] + G_EPS;
+  const float f1 = far[b] + G_EPS;
+  const float n2 = n1 + G_EPS;
+  s_vals[e] = (1.f / t1 - 1.f / n1) / (1.f / f1 - 1.f / n2);
+  if (t_shift) t_shift[e] = t1;
+}
+
+// intern/parameterization.py:10-13
+__global__ void __launch_bounds__(256)
+s_to_t_kernel(const float* __restrict__ s_vals, const float* __restrict__ near, const float* __restrict__ far, int B,
+              int K, float* __restrict__ t_vals) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)B * K) return;
+  const int b = (int)(e / K);
+  const float s = s_vals[e];
+  const float gf = 1.f / (far[b] + G_EPS), gn = 1.f / (near[b] + G_EPS);
+  t_vals[e] = 1.f / ((s * gf + (1.f - s) * gn) + G_EPS);
+}
+
+static inline int ray_grid(int B, int warps) {
+  long long b = ((long long)B + warps - 1) / warps;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mip360
+
+using namespace mip360;
+
+extern "C" {
+
+int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
+                         int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
+                         float* distance, float* acc, float* weights, mip360_stream_t stream) {
+  MIP_REQUIRE(rgb_or_raw && t_vals && dirs && comp_rgb && distance && acc, "composite_fwd: null pointer");
+  MIP_REQUIRE(head_mode == 1 || density, "composite_fwd: density missing");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
+      distance, acc, weights);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
+                         int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
+                         const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in, float* g_density,
+                         float* g_raw, uint16_t* g_raw_bf16, mip360_stream_t stream) {
+  MIP_REQUIRE(rgb_or_raw && t_vals && dirs, "composite_bwd: null pointer");
+  MIP_REQUIRE(head_mode == 1 || density, "composite_bwd: density missing");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
+      g_w, g_rgb_in, g_density, g_raw, g_raw_bf16);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
+                                 int density_mode, float density_bias, float* weights, mip360_stream_t stream) {
+  MIP_REQUIRE(density && t_vals && dirs && weights, "density_to_weight_fwd: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
+      weights);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
+                                 int density_mode, float density_bias, const float* g_w, float* g_density,
+                                 uint16_t* g_raw_bf16, mip360_stream_t stream) {
+  MIP_REQUIRE(density && t_vals && dirs && g_w, "density_to_weight_bwd: null pointer");
+  MIP_REQUIRE(g_density || g_raw_bf16, "density_to_weight_bwd: no output");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, g_w, nullptr,
+      g_density, nullptr, g_raw_bf16);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_t_to_s(const float* t_vals, const float* near, const float* far, int B, int K, float* s_vals,
+                  float* t_shift, mip360_stream_t stream) {
+  MIP_REQUIRE(t_vals && near && far && s_vals, "t_to_s: null pointer");
+  if (B <= 0 || K <= 0) return MIP360_OK;
+  const long long n = (long long)B * K;
+  t_to_s_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t_vals, near, far, B, K, s_vals, t_shift);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_s_to_t(const float* s_vals, const float* near, const float* far, int B, int K, float* t_vals,
+                  mip360_stream_t stream) {
+  MIP_REQUIRE(s_vals && near && far && t_vals, "s_to_t: null pointer");
+  if (B <= 0 || K <= 0) return MIP360_OK;
+  const long long n = (long long)B * K;
+  s_to_t_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s_vals, near, far, B, K, t_vals);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // extern "C"

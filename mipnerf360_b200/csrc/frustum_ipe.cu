@@ -1,0 +1,487 @@
+// K0/K1: level-0 sampling, conical frustum -> Gaussian -> contraction -> integrated positional
+// encoding, fused.  One thread per sample; per-warp shared-memory staging turns the per-sample rows
+// (3, 9, 42 floats or 64 bf16) into fully coalesced 128-byte stores.
+//
+// Compiled with --fmad=false: every fp32 operation is rounded the way the reference's unfused
+// PyTorch elementwise ops round it (reference: intern/parameterization.py, intern/encoding.py).
+#include "common.cuh"
+
+namespace mip360 {
+
+// intern/encoding.py:9-29 — row order defines encoding column order
+__constant__ float c_P[21][3] = {
+    {0.8506508f, 0.f, 0.5257311f},   {0.809017f, 0.5f, 0.309017f},   {0.5257311f, 0.8506508f, 0.f},
+    {1.f, 0.f, 0.f},                 {0.809017f, 0.5f, -0.309017f},  {0.8506508f, 0.f, -0.5257311f},
+    {0.309017f, 0.809017f, -0.5f},   {0.f, 0.5257311f, -0.8506508f}, {0.5f, 0.309017f, -0.809017f},
+    {0.f, 1.f, 0.f},                 {-0.5257311f, 0.8506508f, 0.f}, {-0.309017f, 0.809017f, -0.5f},
+    {0.f, 0.5257311f, 0.8506508f},   {-0.309017f, 0.809017f, 0.5f},  {0.309017f, 0.809017f, 0.5f},
+    {0.5f, 0.309017f, 0.809017f},    {0.5f, -0.309017f, 0.809017f},  {0.f, 0.f, 1.f},
+    {-0.5f, 0.309017f, 0.809017f},   {-0.809017f, 0.5f, 0.309017f},  {-0.809017f, 0.5f, -0.309017f}};
+
+__device__ __forceinline__ float g_disp(float x) { return 1.0f / (x + G_EPS); }  // parameterization.py:15-21
+
+// intern/parameterization.py:101-107 (stable branch)
+__device__ __forceinline__ void frustum_moments(float t0, float t1, float radius, float& t_mean, float& t_var,
+                                                float& r_var) {
+  const float mu = (t0 + t1) / 2.f;
+  const float hw = (t1 - t0) / 2.f;
+  const float mu2 = mu * mu, hw2 = hw * hw;
+  const float hw4 = hw2 * hw2;
+  const float den = 3.f * mu2 + hw2;
+  t_mean = mu + (2.f * mu * hw2) / den;
+  t_var = hw2 / 3.f - (4.f / 15.f) * ((hw4 * (12.f * mu2 - hw2)) / (den * den));
+  r_var = (radius * radius) * (mu2 / 4.f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 / den);
+}
+
+// intern/parameterization.py:45-61 (diag=False)
+__device__ __forceinline__ void lift_to_xyz(const float d[3], float t_mean, float t_var, float r_var, float mean[3],
+                                            float cov[9]) {
+  const float dmag = fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-10f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    mean[i] = d[i] * t_mean;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float d_outer = d[i] * d[j];
+      const float null_outer = (i == j ? 1.f : 0.f) - d[i] * (d[j] / dmag);
+      cov[i * 3 + j] = t_var * d_outer + r_var * null_outer;
+    }
+  }
+}
+
+// cov <- J cov J^T with J = a I + b x x^T (closed form of jacobian(contract, x))
+__device__ __forceinline__ void apply_contract_jacobian(const float x[3], float m, float cov[9]) {
+  const float m2 = m * m;
+  const float a = 2.f / m - 1.f / m2;
+  const float b = -2.f / (m2 * m) + 2.f / (m2 * m2);
+  float J[9], T[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) J[i * 3 + j] = (i == j ? a : 0.f) + b * (x[i] * x[j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      T[i * 3 + j] = J[i * 3 + 0] * cov[0 * 3 + j] + J[i * 3 + 1] * cov[1 * 3 + j] + J[i * 3 + 2] * cov[2 * 3 + j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      cov[i * 3 + j] = T[i * 3 + 0] * J[j * 3 + 0] + T[i * 3 + 1] * J[j * 3 + 1] + T[i * 3 + 2] * J[j * 3 + 2];
+}
+
+// intern/parameterization.py:64-83.  mode 0: reference (global norm n, Jacobian at the scaled mean with the
+// per-point norm), 1: per-point contraction, 2: none.
+__device__ __forceinline__ void contract_gaussian(float mean[3], float cov[9], int mode, float n_global) {
+  if (mode == 0) {
+    if (!(n_global <= 1.f)) {
+      const float c = 2.f - 1.f / n_global;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) mean[i] = c * (mean[i] / n_global);
+    }
+    const float m = sqrtf(mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]);
+    if (m > 1.f) apply_contract_jacobian(mean, m, cov);
+  } else if (mode == 1) {
+    const float m = sqrtf(mean[0] * mean[0] + mean[1] * mean[1] + mean[2] * mean[2]);
+    if (m > 1.f) {
+      apply_contract_jacobian(mean, m, cov);
+      const float c = 2.f - 1.f / m;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) mean[i] = c * (mean[i] / m);
+    }
+  }
+}
+
+// intern/encoding.py:43-55: gamma = P mean, sigma_k = P_k cov P_k^T; has_cov = false gives plain PE
+__device__ __forceinline__ void ipe_features(const float mean[3], const float cov[9], bool has_cov, float* out_sin,
+                                             float* out_cos, int stride) {
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    const float p0 = c_P[k][0], p1 = c_P[k][1], p2 = c_P[k][2];
+    const float gamma = p0 * mean[0] + p1 * mean[1] + p2 * mean[2];
+    float damp = 1.f;
+    if (has_cov) {
+      // A = cov P^T (column k), sigma = sum_i P_ki A_ik
+      const float a0 = cov[0] * p0 + cov[1] * p1 + cov[2] * p2;
+      const float a1 = cov[3] * p0 + cov[4] * p1 + cov[5] * p2;
+      const float a2 = cov[6] * p0 + cov[7] * p1 + cov[8] * p2;
+      const float sigma = p0 * a0 + p1 * a1 + p2 * a2;
+      damp = expf(-0.5f * sigma);
+    }
+    float s, c;
+    sincosf(gamma, &s, &c);
+    out_sin[k * stride] = damp * s;
+    out_cos[k * stride] = damp * c;
+  }
+}
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_STAGE_FLOATS = 32 * 43;  // per-warp staging: 32 rows x (42 + 1 pad) floats
+
+// Write V floats per lane (row-major rows of length V, rows of a warp contiguous in global memory)
+template <int V>
+__device__ __forceinline__ void warp_store_rows(float* stage, const float* vals, float* gbase, int lane,
+                                                int rows_valid) {
+  constexpr int LD = (V % 2 == 0) ? V + 1 : V;  // odd leading dimension -> conflict-free
+#pragma unroll
+  for (int c = 0; c < V; ++c) stage[lane * LD + c] = vals[c];
+  __syncwarp();
+  const int total = rows_valid * V;
+  for (int e = lane; e < total; e += 32) {
+    const int r = e / V, c = e - r * V;
+    gbase[e] = stage[r * LD + c];
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
+                const float* __restrict__ origins, const float* __restrict__ directions,
+                const float* __restrict__ vdir_enc, const float* __restrict__ radii,
+                const double* __restrict__ norm_sq, long long S, int N, int contract_mode, int add_origins,
+                float* __restrict__ means_out, float* __restrict__ covs_out, float* __restrict__ enc_out,
+                uint16_t* __restrict__ x_out) {
+  __shared__ __align__(16) float stage_all[(K1_THREADS / 32) * K1_STAGE_FLOATS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* stage = stage_all + warp * K1_STAGE_FLOATS;
+  const long long warp_s0 = (long long)blockIdx.x * K1_THREADS + warp * 32;
+  if (warp_s0 >= S) return;
+  const long long s = warp_s0 + lane;
+  const bool valid = s < S;
+  const int rows_valid = (int)min((long long)32, S - warp_s0);
+  const long long sc = valid ? s : S - 1;
+  const int b = (int)(sc / N);
+  const int j = (int)(sc - (long long)b * N);
+
+  float n_global = 0.f;
+  if (contract_mode == 0) n_global = (float)sqrt(*norm_sq);
+
+  const float t0 = t0p[(long long)b * t_stride + j];
+  const float t1 = t1p[(long long)b * t_stride + j];
+  float d[3] = {directions[b * 3 + 0], directions[b * 3 + 1], directions[b * 3 + 2]};
+  const float radius = radii[b];
+
+  float t_mean, t_var, r_var, mean[3], cov[9];
+  frustum_moments(t0, t1, radius, t_mean, t_var, r_var);
+  lift_to_xyz(d, t_mean, t_var, r_var, mean, cov);
+  contract_gaussian(mean, cov, contract_mode, n_global);
+  if (add_origins) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mean[i] = mean[i] + origins[b * 3 + i];
+  }
+
+  if (means_out) warp_store_rows<3>(stage, mean, means_out + warp_s0 * 3, lane, rows_valid);
+  if (covs_out) warp_store_rows<9>(stage, cov, covs_out + warp_s0 * 9, lane, rows_valid);
+  if (!enc_out && !x_out) return;
+
+  // features into the staging tile: row = lane, leading dimension 43
+  float* row = stage + lane * 43;
+  ipe_features(mean, cov, true, row, row + 21, 1);
+  __syncwarp();
+  if (enc_out) {
+    float* g = enc_out + warp_s0 * 42;
+    const int total = rows_valid * 42;
+    for (int e = lane; e < total; e += 32) {
+      const int r = e / 42, c = e - r * 42;
+      g[e] = stage[r * 43 + c];
+    }
+  }
+  if (x_out) {
+    // bf16 rows of 64: [0,42) IPE, [42,58) view-direction encoding of the ray, [58,64) zeros.
+    // Each lane converts its own row to 8 x 16-byte chunks, stored XOR-swizzled, then the warp writes
+    // its 4 KB (32 rows x 128 B, contiguous in global memory) with 16-byte coalesced stores.
+    uint32_t packed[32];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) packed[c] = pack_bf16x2(row[2 * c], row[2 * c + 1]);
+    const float4* vd4 = reinterpret_cast<const float4*>(vdir_enc + (long long)b * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = vd4[q];
+      packed[21 + 2 * q] = pack_bf16x2(v.x, v.y);
+      packed[22 + 2 * q] = pack_bf16x2(v.z, v.w);
+    }
+    packed[29] = packed[30] = packed[31] = 0u;
+    __syncwarp();  // everyone is done reading the fp32 staging rows
+    uint4* stage4 = reinterpret_cast<uint4*>(stage);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      stage4[lane * 8 + (c ^ (lane & 7))] =
+          make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+    __syncwarp();
+    uint4* g4 = reinterpret_cast<uint4*>(x_out + warp_s0 * 64);
+    const int total = rows_valid * 8;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int q = it * 32 + lane;
+      if (q < total) {
+        const int r = q >> 3, c = q & 7;
+        g4[q] = stage4[r * 8 + (c ^ (r & 7))];
+      }
+    }
+  }
+}
+
+// Σ |d t_mean|^2 over all samples (App. A1): per-thread fp32 products as the reference forms them,
+// accumulated in fp64.
+__global__ void __launch_bounds__(256)
+frustum_norm_sq_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
+                       const float* __restrict__ directions, long long S, int N, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(s / N);
+    const int j = (int)(s - (long long)b * N);
+    const float t0 = t0p[(long long)b * t_stride + j], t1 = t1p[(long long)b * t_stride + j];
+    float t_mean, t_var, r_var;
+    frustum_moments(t0, t1, 0.f, t_mean, t_var, r_var);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float m = directions[b * 3 + i] * t_mean;
+      acc += (double)m * (double)m;
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += sm[i];
+    atomicAdd(out, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sum_sq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += sm[i];
+    atomicAdd(out, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+contract_kernel(const float* __restrict__ x, long long n, const double* __restrict__ norm_sq, float* __restrict__ y) {
+  const float nrm = (float)sqrt(*norm_sq);
+  const bool ident = nrm <= 1.f;
+  const float c = 2.f - 1.f / nrm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = ident ? x[i] : c * (x[i] / nrm);
+}
+
+__global__ void __launch_bounds__(256)
+gaussian_contract_kernel(const float* __restrict__ mi, const float* __restrict__ ci, const double* __restrict__ norm_sq,
+                         long long S, float* __restrict__ mo, float* __restrict__ co) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float nrm = (float)sqrt(*norm_sq);
+  float mean[3], cov[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) mean[i] = mi[s * 3 + i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) cov[i] = ci[s * 9 + i];
+  contract_gaussian(mean, cov, 0, nrm);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) mo[s * 3 + i] = mean[i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) co[s * 9 + i] = cov[i];
+}
+
+__global__ void __launch_bounds__(256)
+gaussian_to_xyz_kernel(const float* __restrict__ directions, const float* __restrict__ t_mean,
+                       const float* __restrict__ t_var, const float* __restrict__ r_var, long long S, int N,
+                       float* __restrict__ means, float* __restrict__ covs) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int b = (int)(s / N);
+  float d[3] = {directions[b * 3], directions[b * 3 + 1], directions[b * 3 + 2]};
+  float mean[3], cov[9];
+  lift_to_xyz(d, t_mean[s], t_var[s], r_var[s], mean, cov);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) means[s * 3 + i] = mean[i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) covs[s * 9 + i] = cov[i];
+}
+
+__global__ void __launch_bounds__(256)
+ipe_kernel(const float* __restrict__ means, const float* __restrict__ covs, long long S, float* __restrict__ enc) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float mean[3], cov[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) mean[i] = means[s * 3 + i];
+  if (covs) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cov[i] = covs[s * 9 + i];
+  }
+  float out[42];
+  ipe_features(mean, cov, covs != nullptr, out, out + 21, 1);
+#pragma unroll
+  for (int i = 0; i < 42; ++i) enc[s * 42 + i] = out[i];
+}
+
+// intern/encoding.py:79-89
+__global__ void __launch_bounds__(256)
+viewdir_enc_kernel(const float* __restrict__ viewdirs, int B, int min_deg, int max_deg, float* __restrict__ enc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float x = viewdirs[b * 3], y = viewdirs[b * 3 + 1], z = viewdirs[b * 3 + 2];
+  const float theta = acosf(z);
+  const float phi = atanf(y / (x + 1e-6f));
+  const int ns = max_deg - min_deg;
+  float* o = enc + (long long)b * 4 * ns;
+  for (int k = 0; k < ns; ++k) {
+    const float sc = exp2f((float)(min_deg + k));
+    float s, c;
+    sincosf(sc * theta, &s, &c);
+    o[k] = s;
+    o[ns + k] = c;
+    sincosf(sc * phi, &s, &c);
+    o[2 * ns + k] = s;
+    o[3 * ns + k] = c;
+  }
+}
+
+// intern/ray.py:100-111
+__global__ void __launch_bounds__(256)
+level0_t_kernel(const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ s_lin,
+                const float* __restrict__ t_rand, float* __restrict__ t_out, int B, int N) {
+  const int K = N + 1;
+  const long long total = (long long)B * K;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int b = (int)(e / K), i = (int)(e - (long long)b * K);
+  const float gf = g_disp(far[b]), gn = g_disp(near[b]);
+  auto tv = [&](int k) {
+    const float s = s_lin[k];
+    return g_disp(s * gf + (1.f - s) * gn);
+  };
+  const float t = tv(i);
+  if (!t_rand) {
+    t_out[e] = t;
+    return;
+  }
+  // mids = .5*(t[1:]+t[:-1]); upper = [mids, t[-1]]; lower = [t[0], mids]
+  const float upper = (i < N) ? 0.5f * (tv(i + 1) + t) : t;
+  const float lower = (i > 0) ? 0.5f * (t + tv(i - 1)) : t;
+  t_out[e] = lower + (upper - lower) * t_rand[e];
+}
+
+static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+static inline int capped_blocks(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mip360
+
+using namespace mip360;
+
+extern "C" {
+
+int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand, float* t_out,
+                         int B, int N, mip360_stream_t stream) {
+  MIP_REQUIRE(near && far && s_lin && t_out, "level0_t_vals: null pointer");
+  MIP_REQUIRE(B >= 0 && N >= 1, "level0_t_vals: bad sizes B=%d N=%d", B, N);
+  if (B == 0) return MIP360_OK;
+  const long long total = (long long)B * (N + 1);
+  level0_t_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, s_lin, t_rand, t_out, B, N);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const float* directions, int B, int N,
+                           double* norm_sq, mip360_stream_t stream) {
+  MIP_REQUIRE(t0 && t1 && directions && norm_sq, "frustum_norm_sq: null pointer");
+  MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "frustum_norm_sq: bad sizes");
+  if (B == 0) return MIP360_OK;
+  const long long S = (long long)B * N;
+  frustum_norm_sq_kernel<<<capped_blocks(S, 256), 256, 0, (cudaStream_t)stream>>>(t0, t1, t_stride, directions, S, N,
+                                                                                  norm_sq);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
+                    const float* vdir_enc, const float* radii, const double* norm_sq, int B, int N, int contract_mode,
+                    int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16, mip360_stream_t stream) {
+  MIP_REQUIRE(t0 && t1 && directions && radii, "cast_ipe: null pointer");
+  MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "cast_ipe: bad sizes B=%d N=%d stride=%d", B, N, t_stride);
+  MIP_REQUIRE(contract_mode >= 0 && contract_mode <= 2, "cast_ipe: contract_mode %d", contract_mode);
+  MIP_REQUIRE(contract_mode != 0 || norm_sq, "cast_ipe: reference contraction needs norm_sq");
+  MIP_REQUIRE(!add_origins || origins, "cast_ipe: add_origins without origins");
+  MIP_REQUIRE(!x_bf16 || vdir_enc, "cast_ipe: x_bf16 output needs vdir_enc [B,16]");
+  if (B == 0) return MIP360_OK;
+  const long long S = (long long)B * N;
+  cast_ipe_kernel<<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
+      t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
+      enc, x_bf16);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_gaussian_to_xyz(const float* directions, const float* t_mean, const float* t_var, const float* r_var, int B,
+                           int N, float* means, float* covs, mip360_stream_t stream) {
+  MIP_REQUIRE(directions && t_mean && t_var && r_var && means && covs, "gaussian_to_xyz: null pointer");
+  if (B <= 0) return MIP360_OK;
+  const long long S = (long long)B * N;
+  gaussian_to_xyz_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(directions, t_mean, t_var, r_var, S, N,
+                                                                               means, covs);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_sum_sq(const float* x, long long n, double* out, mip360_stream_t stream) {
+  MIP_REQUIRE(x && out, "sum_sq: null pointer");
+  if (n <= 0) return MIP360_OK;
+  sum_sq_kernel<<<capped_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_contract(const float* x, long long n, const double* norm_sq, float* y, mip360_stream_t stream) {
+  MIP_REQUIRE(x && y && norm_sq, "contract: null pointer");
+  if (n <= 0) return MIP360_OK;
+  contract_kernel<<<capped_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, norm_sq, y);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_gaussian_contract(const float* means_in, const float* covs_in, const double* norm_sq, long long S,
+                             float* means_out, float* covs_out, mip360_stream_t stream) {
+  MIP_REQUIRE(means_in && covs_in && norm_sq && means_out && covs_out, "gaussian_contract: null pointer");
+  if (S <= 0) return MIP360_OK;
+  gaussian_contract_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(means_in, covs_in, norm_sq, S,
+                                                                                 means_out, covs_out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_ipe(const float* means, const float* covs, long long S, float* enc, mip360_stream_t stream) {
+  MIP_REQUIRE(means && enc, "ipe: null pointer");
+  if (S <= 0) return MIP360_OK;
+  ipe_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(means, covs, S, enc);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_viewdir_enc(const float* viewdirs, int B, int min_deg, int max_deg, float* enc, mip360_stream_t stream) {
+  MIP_REQUIRE(viewdirs && enc, "viewdir_enc: null pointer");
+  MIP_REQUIRE(max_deg > min_deg, "viewdir_enc: empty scale range");
+  if (B <= 0) return MIP360_OK;
+  viewdir_enc_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(viewdirs, B, min_deg, max_deg, enc);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // extern "C"

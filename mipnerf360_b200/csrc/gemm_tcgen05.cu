@@ -1,0 +1,565 @@
+// K2: the MLP contractions of prop_net / nerf_net (model.py:43-53, :131-158) on 5th-generation tensor
+// cores.  bf16 operands are staged by TMA into 128-byte-swizzled shared memory, tcgen05.mma
+// (M=128, N<=256, K=16 per instruction, issued by one thread) accumulates fp32 in tensor memory, and
+// four epilogue warps read the accumulator back with tcgen05.ld and apply the fused epilogue.
+//
+//   linear_kernel<BN, EPI>   persistent, warp-specialised (TMA warp / MMA warp / 4 epilogue warps),
+//                            4-6 stage smem ring, double-buffered TMEM accumulator:
+//        EPI_FWD    Y = act(X W^T + b)            (bias + ReLU/Sigmoid, bf16 and/or fp32 head output)
+//        EPI_DGRAD  dX = (dY Wt^T) .* act'(Yprev) (activation derivative from the saved output)
+//   wgrad_kernel<BN>         dW = dY^T X with both operands MN-major (the reduction dimension is the
+//                            slow one in memory), split over rays, fp32 vector atomics; the bias
+//                            gradient rides along as one extra N=16 MMA against a tile of ones.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace mip360 {
+
+using namespace ptx;
+
+constexpr int BM = 128;   // UMMA M
+constexpr int BK = 64;    // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+enum { EPI_FWD = 0, EPI_DGRAD = 1 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+
+template <int BN>
+struct LinearCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct LinearParams {
+  const float* bias;       // [N] (EPI_FWD) or null
+  const uint16_t* yprev;   // [M, N] saved activation output (EPI_DGRAD)
+  uint16_t* out_bf16;      // [M, N] or null
+  float* out_f32;          // [M, n_valid] or null
+  int M, N, K, act, n_valid;
+};
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
+  return x;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const LinearParams p) {
+  using Cfg = LinearCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
+  const int total_tiles = tiles_m * tiles_n;
+  const int kblocks = p.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to warp with (warp % 4) == q =====
+    const int q = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        float x[32];
+        if (EPI == EPI_FWD) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            x[4 * i + 0] = act_fwd(__uint_as_float(v[4 * i + 0]) + bb.x, p.act);
+            x[4 * i + 1] = act_fwd(__uint_as_float(v[4 * i + 1]) + bb.y, p.act);
+            x[4 * i + 2] = act_fwd(__uint_as_float(v[4 * i + 2]) + bb.z, p.act);
+            x[4 * i + 3] = act_fwd(__uint_as_float(v[4 * i + 3]) + bb.w, p.act);
+          }
+        } else {
+          // dX = acc .* act'(y), y = saved output of the layer whose input gradient this is
+          uint4 yv[4];
+          if (row_ok) {
+            const uint4* y4 = reinterpret_cast<const uint4*>(p.yprev + (size_t)row * p.N + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yv[i] = __ldg(y4 + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yv[i] = make_uint4(0, 0, 0, 0);
+          }
+          const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
+            float d_lo, d_hi;
+            if (p.act == ACT_RELU) {
+              d_lo = y_lo > 0.f ? 1.f : 0.f;
+              d_hi = y_hi > 0.f ? 1.f : 0.f;
+            } else if (p.act == ACT_SIGMOID) {
+              d_lo = y_lo * (1.f - y_lo);
+              d_hi = y_hi * (1.f - y_hi);
+            } else {
+              d_lo = d_hi = 1.f;
+            }
+            x[2 * i] = __uint_as_float(v[2 * i]) * d_lo;
+            x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * d_hi;
+          }
+        }
+        if (row_ok) {
+          if (p.out_bf16) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.N + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(pack_bf16x2(x[8 * i], x[8 * i + 1]), pack_bf16x2(x[8 * i + 2], x[8 * i + 3]),
+                                 pack_bf16x2(x[8 * i + 4], x[8 * i + 5]), pack_bf16x2(x[8 * i + 6], x[8 * i + 7]));
+          }
+          if (p.out_f32 && col0 == 0) {
+            float* o = p.out_f32 + (size_t)row * p.n_valid;
+            if (p.n_valid == 4) {
+              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.n_valid) o[i] = x[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[N_out, K_in] += dY[M, N_out]^T X[M, K_in], db[N_out] += colsum(dY).
+// MMA M <- 128 output features, MMA N <- BN input features, reduction over rows of dY / X in blocks
+// of 64.  Both operands are MN-major: a TMA box is [64 rows x 64 contiguous features] (8 KB, 128-byte
+// swizzle): descriptor SBO = 1024 B between 8-row groups along the reduction, LBO = 8192 B between
+// 64-feature chunks; one K=16 MMA consumes two 8-row groups (2048 B).
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct WgradCfg {
+  static constexpr int BOX_BYTES = 64 * 64 * 2;  // 8 KB
+  static constexpr int A_BYTES = 2 * BOX_BYTES;  // 128 output features
+  static constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int ONES_BYTES = 2048;
+  static constexpr int TMEM_COLS = (BN >= 256) ? 512 : (BN >= 128 ? 256 : 128);  // BN accumulator columns + 16 (bias gradient)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + 1024 + 256;
+};
+
+struct WgradParams {
+  float* dW;  // [N_out, K_in] fp32, accumulated into
+  float* db;  // [N_out] or null
+  int M, N_out, K_in, splits;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+             const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ones_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = ones_base + Cfg::ONES_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = p.K_in / BN;               // along input features
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int f0 = (tile / tiles_n) * BM;          // output-feature offset (rows of dW)
+  const int i0 = (tile % tiles_n) * BN;          // input-feature offset (cols of dW)
+  const int kb_total = (p.M + BK - 1) / BK;
+  const int kb_begin = (int)((long long)kb_total * split / p.splits);
+  const int kb_end = (int)((long long)kb_total * (split + 1) / p.splits);
+  const int nkb = kb_end - kb_begin;
+  const bool do_bias = (p.db != nullptr) && (i0 == 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_x);
+  }
+  // tile of bf16 ones (0x3F80) for the bias-gradient MMA
+  for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += GEMM_THREADS)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(sa + c * Cfg::BOX_BYTES, &tmap_dy, full_bar(stage), f0 + c * 64, kb * BK);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sa + Cfg::A_BYTES + c * Cfg::BOX_BYTES, &tmap_x, full_bar(stage), i0 + c * 64, kb * BK);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1);
+        constexpr uint32_t idesc_ones = make_idesc_bf16(16, 1, 1);
+        const uint64_t ones_desc = make_smem_desc_sw128(ones_base, Cfg::BOX_BYTES, 1024);
+        uint32_t stage = 0, phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, Cfg::BOX_BYTES, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::A_BYTES, Cfg::BOX_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // 16 reduction rows = 2 x 1024 B groups: +128 in the (addr >> 4) field
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16(tmem_base, adesc + 128u * k, bdesc + 128u * k, idesc, accum);
+            if (do_bias) umma_bf16(tmem_base + BN, adesc + 128u * k, ones_desc, idesc_ones, accum);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = f0 + q * 32 + lane;  // output feature
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (row < p.N_out) {
+          float* dst = p.dW + (size_t)row * p.K_in + i0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            red_add_v4(dst + 4 * i, __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      if (do_bias) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + BN, v);  // columns BN..BN+15 hold the bias gradient (all equal)
+        tmem_ld_wait();
+        if (row < p.N_out) atomicAdd(p.db + row, __uint_as_float(v[0]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// fp32 [N,K] -> bf16 [Npad,Kpad] (+ transposed [Kpad,Npad]), zero padded
+__global__ void __launch_bounds__(256)
+cast_weight_kernel(const float* __restrict__ W, int N, int K, int Npad, int Kpad, uint16_t* __restrict__ Wb,
+                   uint16_t* __restrict__ Wt) {
+  const long long total = (long long)Npad * Kpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / Kpad), k = (int)(e - (long long)n * Kpad);
+    const float v = (n < N && k < K) ? W[(long long)n * K + k] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    const uint16_t bits = *reinterpret_cast<const uint16_t*>(&b);
+    if (Wb) Wb[e] = bits;
+    if (Wt) Wt[(long long)k * Npad + n] = bits;
+  }
+}
+
+// fused AdamW (torch.optim.AdamW semantics: decoupled decay, bias-corrected moments)
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+// ---- host side: tensor maps ------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols]; box = [box_rows, 64 cols], 128-byte swizzle, OOB reads give zeros
+static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MIP360_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d ptr=%p", (int)r, rows, cols, box_rows,
+              ptr);
+    return MIP360_ERR_CUDA;
+  }
+  return MIP360_OK;
+}
+
+template <int BN, int EPI>
+static int launch_linear(const uint16_t* A, const uint16_t* Bw, const LinearParams& p, cudaStream_t stream) {
+  using Cfg = LinearCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap(&ta, A, p.M, p.K, BM)) != MIP360_OK) return rc;
+  if ((rc = make_tmap(&tb, Bw, p.N, p.K, BN)) != MIP360_OK) return rc;
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  linear_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+template <int EPI>
+static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const LinearParams& p, cudaStream_t stream) {
+  if (p.N % 256 == 0) return launch_linear<256, EPI>(A, Bw, p, stream);
+  if (p.N == 128) return launch_linear<128, EPI>(A, Bw, p, stream);
+  if (p.N == 64) return launch_linear<64, EPI>(A, Bw, p, stream);
+  set_error("linear: N=%d not supported (need 64, 128 or a multiple of 256)", p.N);
+  return MIP360_ERR_UNSUPPORTED;
+}
+
+template <int BN>
+static int launch_wgrad(const uint16_t* dY, const uint16_t* X, WgradParams p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MIP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap tdy, tx;
+  int rc;
+  if ((rc = make_tmap(&tdy, dY, p.M, p.N_out, 64)) != MIP360_OK) return rc;
+  if ((rc = make_tmap(&tx, X, p.M, p.K_in, 64)) != MIP360_OK) return rc;
+  const int tiles = ((p.N_out + BM - 1) / BM) * (p.K_in / BN);
+  const int kb_total = (p.M + BK - 1) / BK;
+  // two waves of CTAs when there is enough reduction depth, at least 8 k-blocks per split
+  int splits = (2 * sm_count()) / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total / 8) splits = kb_total / 8 > 0 ? kb_total / 8 : 1;
+  p.splits = splits;
+  wgrad_kernel<BN><<<tiles * splits, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tdy, tx, p);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // namespace mip360
+
+using namespace mip360;
+
+extern "C" {
+
+int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
+                      uint16_t* out_bf16, float* out_f32, int n_valid, mip360_stream_t stream) {
+  MIP_REQUIRE(X && W && bias, "linear_fwd: null pointer");
+  MIP_REQUIRE(out_bf16 || out_f32, "linear_fwd: no output");
+  MIP_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "linear_fwd: bad shape M=%d N=%d K=%d (K %% 64 != 0?)", M, N, K);
+  MIP_REQUIRE(!out_f32 || (n_valid >= 1 && n_valid <= 8), "linear_fwd: n_valid=%d outside [1,8]", n_valid);
+  MIP_REQUIRE(act >= 0 && act <= 2, "linear_fwd: act=%d", act);
+  LinearParams p{bias, nullptr, out_bf16, out_f32, M, N, K, act, n_valid};
+  return dispatch_linear<EPI_FWD>(X, W, p, (cudaStream_t)stream);
+}
+
+int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,
+                        uint16_t* dX, mip360_stream_t stream) {
+  // GEMM view: out[M, K] = dY[M, N] * Wt[K, N]^T : reduction over N, output width K
+  MIP_REQUIRE(dY && Wt && dX, "linear_dgrad: null pointer");
+  MIP_REQUIRE(act == ACT_NONE || Yprev, "linear_dgrad: activation derivative needs Yprev");
+  MIP_REQUIRE(M > 0 && N > 0 && K > 0 && N % BK == 0, "linear_dgrad: bad shape M=%d N=%d K=%d (N %% 64 != 0?)", M, N, K);
+  LinearParams p{nullptr, Yprev, dX, nullptr, M, /*N=*/K, /*K=*/N, act, 0};
+  return dispatch_linear<EPI_DGRAD>(dY, Wt, p, (cudaStream_t)stream);
+}
+
+int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int K, float* dW, float* db,
+                        mip360_stream_t stream) {
+  MIP_REQUIRE(dY && X && dW, "linear_wgrad: null pointer");
+  MIP_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0 && K % 64 == 0, "linear_wgrad: bad shape M=%d N=%d K=%d", M, N, K);
+  WgradParams p{dW, db, M, N, K, 1};
+  if (K % 256 == 0) return launch_wgrad<256>(dY, X, p, (cudaStream_t)stream);
+  if (K == 128) return launch_wgrad<128>(dY, X, p, (cudaStream_t)stream);
+  if (K == 64) return launch_wgrad<64>(dY, X, p, (cudaStream_t)stream);
+  set_error("linear_wgrad: K=%d not supported (need 64, 128 or a multiple of 256)", K);
+  return MIP360_ERR_UNSUPPORTED;
+}
+
+int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_t* Wb, uint16_t* Wt,
+                       mip360_stream_t stream) {
+  MIP_REQUIRE(W && (Wb || Wt), "cast_weight: null pointer");
+  MIP_REQUIRE(N > 0 && K > 0 && Npad >= N && Kpad >= K, "cast_weight: bad shape");
+  const long long total = (long long)Npad * Kpad;
+  int grid = (int)((total + 255) / 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  cast_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, N, K, Npad, Kpad, Wb, Wt);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, mip360_stream_t stream) {
+  MIP_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  int grid = (int)((n + 255) / 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+// K5 distortion regulariser (intern/regularization.py:3-19) and K6 interlevel loss
+// (intern/distillation.py:4-51), forward and backward, one warp per ray, O(N) per ray instead of the
+// reference's O(N^2) / O(N) Python loops.  Prefix sums that are later differenced are carried in fp64
+// so that the cancellation does not cost fp32 accuracy.
+#include "common.cuh"
+
+namespace mip360 {
+
+constexpr int LS_WARPS = 4;
+constexpr int LS_MAXC = (MIP360_MAX_SAMPLES + 31) / 32;
+constexpr int LS_MAX_PARTIALS = 4096;
+
+__device__ __forceinline__ double warp_scan_incl_d(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double n = __shfl_up_sync(FULL_MASK, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+struct __align__(16) DistSmem {
+  float s[MIP360_MAX_SAMPLES + 1];
+  float w[MIP360_MAX_SAMPLES];
+};
+
+// per-ray: 2 sum_i w_i (m_i W_<i - (wm)_<i) + 1/3 sum_i w_i^2 ds_i   (m sorted, App. A9)
+template <bool BWD>
+__global__ void __launch_bounds__(LS_WARPS * 32)
+distortion_kernel(const float* __restrict__ s_vals, const float* __restrict__ weights, int B, int N,
+                  float* __restrict__ per_ray, double* __restrict__ partials, const float* __restrict__ g_loss_ptr,
+                  float* __restrict__ g_w) {
+  __shared__ DistSmem sm[LS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  DistSmem& s = sm[warp];
+  const int C = (N + 31) >> 5, j0 = lane * C;
+  double block_acc = 0.0;
+  float g_loss = 1.f;
+  if (BWD) g_loss = *g_loss_ptr;
+  for (int b = blockIdx.x * LS_WARPS + warp; b < B; b += gridDim.x * LS_WARPS) {
+    for (int k = lane; k <= N; k += 32) s.s[k] = s_vals[(long long)b * (N + 1) + k];
+    for (int j = lane; j < N; j += 32) s.w[j] = weights[(long long)b * N + j];
+    __syncwarp();
+    double eW[LS_MAXC], eWM[LS_MAXC];
+    float m[LS_MAXC], w[LS_MAXC], ds[LS_MAXC];
+    double runW = 0.0, runWM = 0.0;
+#pragma unroll
+    for (int c = 0; c < LS_MAXC; ++c) {
+      const int j = j0 + c;
+      m[c] = w[c] = ds[c] = 0.f;
+      if (c < C && j < N) {
+        m[c] = 0.5f * (s.s[j] + s.s[j + 1]);
+        ds[c] = s.s[j + 1] - s.s[j];
+        w[c] = s.w[j];
+      }
+      eW[c] = runW;
+      eWM[c] = runWM;
+      runW += (double)w[c];
+      runWM += (double)w[c] * (double)m[c];
+    }
+    const double inclW = warp_scan_incl_d(runW, lane), inclWM = warp_scan_incl_d(runWM, lane);
+    const double offW = inclW - runW, offWM = inclWM - runWM;
+    if (!BWD) {
+      double loss = 0.0;
+#pragma unroll
+      for (int c = 0; c < LS_MAXC; ++c) {
+        const double Wl = offW + eW[c], WMl = offWM + eWM[c];
+        loss += 2.0 * (double)w[c] * ((double)m[c] * Wl - WMl) + (double)w[c] * (double)w[c] * (double)ds[c] / 3.0;
+      }
+      loss = warp_sum(loss);
+      if (lane == 0) {
+        if (per_ray) per_ray[b] = (float)loss;
+        block_acc += loss;
+      }
+    } else {
+      const double Wtot = __shfl_sync(FULL_MASK, inclW, 31), WMtot = __shfl_sync(FULL_MASK, inclWM, 31);
+#pragma unroll
+      for (int c = 0; c < LS_MAXC; ++c) {
+        const int j = j0 + c;
+        if (c < C && j < N) {
+          const double Wl = offW + eW[c], WMl = offWM + eWM[c];
+          const double Wr = Wtot - Wl - (double)w[c], WMr = WMtot - WMl - (double)w[c] * (double)m[c];
+          // d/dw_i = 2 sum_j w_j |m_i - m_j| + 2/3 w_i ds_i
+          const double g = 2.0 * ((double)m[c] * (Wl - Wr) - (WMl - WMr)) + (2.0 / 3.0) * (double)w[c] * (double)ds[c];
+          g_w[(long long)b * N + j] = (float)(g * (double)g_loss);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!BWD) {
+    __shared__ double sm_part[LS_WARPS];
+    if (lane == 0) sm_part[warp] = block_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < LS_WARPS; ++i) t += sm_part[i];
+      partials[blockIdx.x] = t;
+    }
+  }
+}
+
+// final deterministic reduction of per-block partial sums
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int n, double scale,
+                                                              float* __restrict__ out) {
+  __shared__ double sm[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += partials[i];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(sm[0] * scale);
+}
+
+struct __align__(16) BoundsSmem {
+  float tf[MIP360_MAX_SAMPLES + 1];
+  float tc[MIP360_MAX_SAMPLES + 1];
+  double cumw[MIP360_MAX_SAMPLES + 1];
+};
+
+// b[r,i] = sum_j w_j [t0_j <= R_i and t1_j >= L_i]  (closed intervals; distillation.py:25-29, App. B5)
+__global__ void __launch_bounds__(LS_WARPS * 32)
+bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
+              int B, int N, float* __restrict__ b_out) {
+  __shared__ BoundsSmem sm[LS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  BoundsSmem& s = sm[warp];
+  const int C = (N + 31) >> 5, j0 = lane * C;
+  for (int b = blockIdx.x * LS_WARPS + warp; b < B; b += gridDim.x * LS_WARPS) {
+    for (int k = lane; k <= N; k += 32) {
+      s.tf[k] = t_fine[(long long)b * (N + 1) + k];
+      s.tc[k] = t_coarse[(long long)b * (N + 1) + k];
+    }
+    // exclusive prefix sums of the fine weights in fp64
+    double run = 0.0, ex[LS_MAXC];
+#pragma unroll
+    for (int c = 0; c < LS_MAXC; ++c) {
+      const int j = j0 + c;
+      ex[c] = run;
+      if (c < C && j < N) run += (double)w_fine[(long long)b * N + j];
+    }
+    const double incl = warp_scan_incl_d(run, lane);
+    const double off = incl - run;
+#pragma unroll
+    for (int c = 0; c < LS_MAXC; ++c) {
+      const int j = j0 + c;
+      if (c < C && j < N) s.cumw[j] = off + ex[c];
+    }
+    if (lane == 31) s.cumw[N] = incl;
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      const float L = s.tc[i], R = s.tc[i + 1];
+      // lo = first j in [0,N) with t1_j = tf[j+1] >= L
+      int lo = 0, hi = N;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s.tf[mid + 1] >= L) hi = mid; else lo = mid + 1;
+      }
+      const int first = lo;
+      // last j with t0_j = tf[j] <= R  -> count of j in [0,N) with tf[j] <= R, minus 1
+      lo = 0; hi = N;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s.tf[mid] <= R) lo = mid + 1; else hi = mid;
+      }
+      const int last = lo - 1;
+      float v = 0.f;
+      if (last >= first) v = (float)(s.cumw[last + 1] - s.cumw[first]);
+      b_out[(long long)b * N + i] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// column sums over rays, accumulated in fp64 into bound_total[N]
+__global__ void __launch_bounds__(256)
+bounds_reduce_kernel(const float* __restrict__ b, int B, int N, int rows_per_block, double* __restrict__ total) {
+  // blockDim = (128, 2): x over columns, y over row parity
+  __shared__ double sm[2][MIP360_MAX_SAMPLES];
+  const int n = threadIdx.x, y = threadIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(B, r0 + rows_per_block);
+  double a = 0.0;
+  if (n < N)
+    for (int r = r0 + y; r < r1; r += 2) a += (double)b[(long long)r * N + n];
+  sm[y][n] = a;
+  __syncthreads();
+  if (y == 0 && n < N) atomicAdd(&total[n], sm[0][n] + sm[1][n]);
+}
+
+// loss = sum relu(bnd - w)^2 / (w + 1e-6) / batch_div   (distillation.py:48-49)
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+interlevel_kernel(const float* __restrict__ w_hat, const float* __restrict__ b_per_ray,
+                  const double* __restrict__ bound_total, long long total, int N, int bound_mode, float batch_div,
+                  double* __restrict__ partials, const float* __restrict__ g_loss_ptr, float* __restrict__ g_w_hat) {
+  double acc = 0.0;
+  float g_scale = 0.f;
+  if (BWD) g_scale = *g_loss_ptr / batch_div;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % N);
+    const float bnd = bound_mode == 0 ? (float)bound_total[i] : b_per_ray[e];
+    const float w = w_hat[e];
+    const float r = fmaxf(bnd - w, 0.f);
+    const float den = w + 1e-6f;
+    if (!BWD) {
+      acc += (double)((r * r) / den);
+    } else {
+      // d/dw [ r^2/(w+eps) ] = -2 r/(w+eps) - r^2/(w+eps)^2
+      g_w_hat[e] = g_scale * (-2.f * r / den - (r * r) / (den * den));
+    }
+  }
+  if (!BWD) block_sum_to_partial<256>(acc, partials);
+}
+
+static inline int ray_grid(int B, int warps) {
+  long long b = ((long long)B + warps - 1) / warps;
+  const long long cap = min((long long)sm_count() * 16, (long long)LS_MAX_PARTIALS);
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mip360
+
+using namespace mip360;
+
+extern "C" {
+
+int mip360_partials_len(int B) {
+  (void)B;
+  return LS_MAX_PARTIALS;
+}
+
+int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int N, float* per_ray, double* partials,
+                          float* loss, mip360_stream_t stream) {
+  MIP_REQUIRE(s_vals && weights && partials && loss, "distortion_fwd: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  MIP_REQUIRE(B >= 0, "distortion_fwd: B=%d", B);
+  const int grid = B > 0 ? ray_grid(B, LS_WARPS) : 0;
+  if (grid > 0) {
+    distortion_kernel<false><<<grid, LS_WARPS * 32, 0, (cudaStream_t)stream>>>(s_vals, weights, B, N, per_ray, partials,
+                                                                                nullptr, nullptr);
+    MIP_LAUNCH_CHECK();
+  }
+  reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0, loss);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int N, const float* g_loss_ptr, float* g_w,
+                          mip360_stream_t stream) {
+  MIP_REQUIRE(s_vals && weights && g_loss_ptr && g_w, "distortion_bwd: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  distortion_kernel<true><<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N, float* b_out,
+                          mip360_stream_t stream) {
+  MIP_REQUIRE(t_fine && w_fine && t_coarse && b_out, "bounds_per_ray: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_per_ray: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, (cudaStream_t)stream>>>(t_fine, w_fine, t_coarse, B, N,
+                                                                                   b_out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_bounds_reduce(const float* b, int B, int N, double* bound_total, mip360_stream_t stream) {
+  MIP_REQUIRE(b && bound_total, "bounds_reduce: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_reduce: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  const int target_blocks = sm_count() * 4;
+  int rows = (B + target_blocks - 1) / target_blocks;
+  if (rows < 16) rows = 16;
+  const int grid = (B + rows - 1) / rows;
+  bounds_reduce_kernel<<<grid, dim3(128, 2), 0, (cudaStream_t)stream>>>(b, B, N, rows, bound_total);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_interlevel_fwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
+                          int bound_mode, float batch_div, double* partials, float* loss, mip360_stream_t stream) {
+  MIP_REQUIRE(w_hat && partials && loss, "interlevel_fwd: null pointer");
+  MIP_REQUIRE(bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr, "interlevel_fwd: bound missing");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "interlevel_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  const long long total = (long long)B * N;
+  int grid = 0;
+  if (total > 0) {
+    grid = (int)min((total + 255) / 256, (long long)min(sm_count() * 8, LS_MAX_PARTIALS));
+    interlevel_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(w_hat, b_per_ray, bound_total, total, N,
+                                                                      bound_mode, batch_div, partials, nullptr, nullptr);
+    MIP_LAUNCH_CHECK();
+  }
+  reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0 / (double)batch_div, loss);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_interlevel_bwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
+                          int bound_mode, float batch_div, const float* g_loss_ptr, float* g_w_hat,
+                          mip360_stream_t stream) {
+  MIP_REQUIRE(w_hat && g_loss_ptr && g_w_hat, "interlevel_bwd: null pointer");
+  MIP_REQUIRE(bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr, "interlevel_bwd: bound missing");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "interlevel_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  const long long total = (long long)B * N;
+  if (total <= 0) return MIP360_OK;
+  const int grid = (int)min((total + 255) / 256, (long long)sm_count() * 8);
+  interlevel_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(w_hat, b_per_ray, bound_total, total, N, bound_mode,
+                                                                   batch_div, nullptr, g_loss_ptr, g_w_hat);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// K4: hierarchical resampling (intern/ray.py:12-57, :118-153).  One warp per ray; the ray's weights,
+// CDF and bin edges are staged in shared memory, the CDF is a lane-chunked warp scan and the inverse
+// CDF a binary search per output sample.  Compiled with --fmad=false so that the lerp and the CDF
+// arithmetic round like the reference's unfused ops: given the same fp32 CDF and uniforms, the bin
+// indices and samples are bit-identical to the reference's mask/max/min formulation (App. B2).
+#include "common.cuh"
+
+namespace mip360 {
+
+constexpr int RS_WARPS = 4;
+constexpr int RS_MAXK = MIP360_MAX_SAMPLES + 1;  // knots
+
+struct __align__(16) ResampleSmem {
+  float wpad[MIP360_MAX_SAMPLES + 2];
+  float w[MIP360_MAX_SAMPLES];
+  float cdf[RS_MAXK];
+  float bins[RS_MAXK];
+};
+
+// ray.py:137-142: w_pad = [w0, w, w_{N-1}]; w_max = max(adjacent) [N+1]; blur = .5*(adjacent) [N]; + padding
+__device__ __forceinline__ void warp_blur(const float* wpad, float* wout, int N, float padding, int lane) {
+  for (int j = lane; j < N; j += 32) {
+    const float m0 = fmaxf(wpad[j], wpad[j + 1]);
+    const float m1 = fmaxf(wpad[j + 1], wpad[j + 2]);
+    wout[j] = 0.5f * (m0 + m1) + padding;
+  }
+}
+
+// ray.py:15-27 on w[N] (shared memory) -> cdf[N+1]
+__device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int lane) {
+  const int C = (N + 31) >> 5;  // contiguous chunk per lane
+  const int j0 = lane * C;
+  float loc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const int j = j0 + c;
+    if (j < N) loc += w[j];
+  }
+  float wsum = warp_sum(loc);
+  const float eps = 1e-5f;
+  const float padding = fmaxf(0.f, eps - wsum);
+  const float add = padding / (float)N;
+  wsum = wsum + padding;
+  // pdf and its inclusive scan
+  float run = 0.f;
+  float pdf_loc[(MIP360_MAX_SAMPLES + 31) / 32];
+#pragma unroll
+  for (int c = 0; c < (MIP360_MAX_SAMPLES + 31) / 32; ++c) {
+    const int j = j0 + c;
+    float p = 0.f;
+    if (c < C && j < N) p = (w[j] + add) / wsum;
+    run += p;
+    pdf_loc[c] = run;  // inclusive within the chunk
+  }
+  const float incl = warp_scan_incl(run, lane);
+  const float off = incl - run;
+#pragma unroll
+  for (int c = 0; c < (MIP360_MAX_SAMPLES + 31) / 32; ++c) {
+    const int j = j0 + c;
+    if (c < C && j < N - 1) cdf[j + 1] = fminf(1.f, off + pdf_loc[c]);
+  }
+  if (lane == 0) {
+    cdf[0] = 0.f;
+    cdf[N] = 1.f;
+  }
+}
+
+// ray.py:41-56: last knot with cdf <= u (upper_bound - 1), lerp inside the interval
+__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int N, float u, int* idx_out) {
+  int lo = 0, hi = N + 1;  // first k in [0, N+1) with cdf[k] > u
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  int i0 = lo - 1;
+  i0 = i0 < 0 ? 0 : i0;  // u < cdf[0] cannot happen for u >= 0; the reference then falls back to knot 0
+  const int i1 = (lo > N) ? N : lo;
+  const float c0 = cdf[i0], c1 = cdf[i1];
+  const float b0 = bins[i0], b1 = bins[i1];
+  float t = nan_to_num_f((u - c0) / (c1 - c0), 0.f);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  if (idx_out) *idx_out = i0;
+  return b0 + t * (b1 - b0);
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
+                const float* __restrict__ jitter, int B, int N, float padding, int blur,
+                float* __restrict__ new_t) {
+  __shared__ ResampleSmem sm[RS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ResampleSmem& s = sm[warp];
+  const int K = N + 1;
+  const float one_m_eps = 1.f - 1.1920928955078125e-07f;
+  for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
+    const float* wrow = weights + (long long)b * N;
+    const float* trow = t_vals + (long long)b * K;
+    for (int j = lane; j < N; j += 32) s.wpad[j + 1] = wrow[j];
+    for (int k = lane; k < K; k += 32) s.bins[k] = trow[k];
+    if (lane == 0) {
+      s.wpad[0] = wrow[0];
+      s.wpad[N + 1] = wrow[N - 1];
+    }
+    __syncwarp();
+    if (blur) {
+      warp_blur(s.wpad, s.w, N, padding, lane);
+    } else {
+      for (int j = lane; j < N; j += 32) s.w[j] = s.wpad[j + 1];
+    }
+    __syncwarp();
+    warp_cdf(s.w, s.cdf, N, lane);
+    __syncwarp();
+    for (int m = lane; m < K; m += 32) {
+      float u = u_base[m];
+      if (jitter) {
+        u = (u + u) + jitter[(long long)b * K + m];  // the doubled stratum offset is the reference's (App. A5)
+        u = fminf(u, one_m_eps);
+      }
+      new_t[(long long)b * K + m] = invert_one(s.cdf, s.bins, N, u, nullptr);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+blur_kernel(const float* __restrict__ weights, int B, int N, float padding, float* __restrict__ out) {
+  __shared__ ResampleSmem sm[RS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ResampleSmem& s = sm[warp];
+  for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
+    const float* wrow = weights + (long long)b * N;
+    for (int j = lane; j < N; j += 32) s.wpad[j + 1] = wrow[j];
+    if (lane == 0) {
+      s.wpad[0] = wrow[0];
+      s.wpad[N + 1] = wrow[N - 1];
+    }
+    __syncwarp();
+    warp_blur(s.wpad, s.w, N, padding, lane);
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) out[(long long)b * N + j] = s.w[j];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+cdf_kernel(const float* __restrict__ weights, int B, int N, float* __restrict__ cdf) {
+  __shared__ ResampleSmem sm[RS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ResampleSmem& s = sm[warp];
+  for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
+    for (int j = lane; j < N; j += 32) s.w[j] = weights[(long long)b * N + j];
+    __syncwarp();
+    warp_cdf(s.w, s.cdf, N, lane);
+    __syncwarp();
+    for (int k = lane; k <= N; k += 32) cdf[(long long)b * (N + 1) + k] = s.cdf[k];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+invert_kernel(const float* __restrict__ bins, const float* __restrict__ cdf, const float* __restrict__ u,
+              int u_row_stride, int B, int N, int M, float* __restrict__ samples, int32_t* __restrict__ idx) {
+  __shared__ ResampleSmem sm[RS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ResampleSmem& s = sm[warp];
+  const int K = N + 1;
+  for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
+    for (int k = lane; k < K; k += 32) {
+      s.cdf[k] = cdf[(long long)b * K + k];
+      s.bins[k] = bins[(long long)b * K + k];
+    }
+    __syncwarp();
+    for (int m = lane; m < M; m += 32) {
+      int i0;
+      const float x = invert_one(s.cdf, s.bins, N, u[(long long)b * u_row_stride + m], &i0);
+      samples[(long long)b * M + m] = x;
+      if (idx) idx[(long long)b * M + m] = i0;
+    }
+    __syncwarp();
+  }
+}
+
+static inline int ray_grid(int B, int warps) {
+  long long b = ((long long)B + warps - 1) / warps;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mip360
+
+using namespace mip360;
+
+extern "C" {
+
+int mip360_blur_weights(const float* weights, int B, int N, float resample_padding, float* out,
+                        mip360_stream_t stream) {
+  MIP_REQUIRE(weights && out, "blur_weights: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "blur_weights: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  blur_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, resample_padding, out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_resample_cdf(const float* weights, int B, int N, float* cdf, mip360_stream_t stream) {
+  MIP_REQUIRE(weights && cdf, "resample_cdf: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample_cdf: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  cdf_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, cdf);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_resample_invert(const float* bins, const float* cdf, const float* u, int u_row_stride, int B, int N, int M,
+                           float* samples, int32_t* idx, mip360_stream_t stream) {
+  MIP_REQUIRE(bins && cdf && u && samples, "resample_invert: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample_invert: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  MIP_REQUIRE(M >= 1, "resample_invert: M=%d", M);
+  if (B <= 0) return MIP360_OK;
+  invert_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(bins, cdf, u, u_row_stride, B, N, M,
+                                                                                   samples, idx);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter, int B, int N,
+                    float resample_padding, int blur, float* new_t, mip360_stream_t stream) {
+  MIP_REQUIRE(t_vals && weights && u_base && new_t, "resample: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  if (B <= 0) return MIP360_OK;
+  resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t_vals, weights, u_base, jitter, B, N, resample_padding, blur, new_t);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Library-wide state: last-error message, launch counter, device properties.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+
+namespace mip360 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+}  // namespace mip360
+
+extern "C" {
+const char* mip360_last_error(void) { return mip360::g_err; }
+int mip360_version(void) { return 100; }
+long long mip360_launch_count(void) { return mip360::g_launches.load(); }
+void mip360_reset_launch_count(void) { mip360::g_launches.store(0); }
+int mip360_sm_count(void) { return mip360::sm_count(); }
+}
