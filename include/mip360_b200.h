@@ -67,14 +67,15 @@ int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin
  *                  1 = per-point contraction (paper), 2 = no contraction.
  *   add_origins: 1 = means += origins after the contraction (para_rays, App. A2); 0 = not
  *     (conical_frustum_to_gaussian itself).
- *   Outputs, each may be NULL: means [S,3], covs [S,3,3], enc [S,42] (fp32, needs means/covs
- *     semantics of the reference: IPE of the returned mean and cov), x_bf16 [S,64] = the MLP
- *     input row: 42 IPE features, 16 view-direction features, 6 zeros, rounded to bf16.
+ *   vdir_enc [B,16] = mip360_viewdir_enc of the rays' view directions (needed for x_bf16 only).
+ *   Outputs, each may be NULL: means [S,3], covs [S,3,3], enc [S,42] (fp32 IPE of the returned
+ *     mean and cov), x_bf16 [S,64] = the MLP input row: 42 IPE features, 16 view-direction
+ *     features, 6 zeros, rounded to bf16.
  * ------------------------------------------------------------------------------------------ */
 int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const float* directions, int B, int N,
                            double* norm_sq, mip360_stream_t stream);
 int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
-                    const float* viewdirs, const float* radii, const double* norm_sq, int B, int N,
+                    const float* vdir_enc, const float* radii, const double* norm_sq, int B, int N,
                     int contract_mode, int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16,
                     mip360_stream_t stream);
 
@@ -122,9 +123,12 @@ int mip360_resample(const float* t_vals, const float* weights, const float* u_ba
  *   weights-only variant (density_to_weight): density_mode 0 = density given, 1 = raw logits,
  *     density = softplus(raw + density_bias) (model.py:92).
  *   Backward: g_rgb [B,3], g_acc [B], g_w [B,N] (any may be NULL) -> gradient w.r.t. rgb/density
- *     (head_mode 0: g_rgb_in [B,N,3], g_density [B,N]) or raw (head_mode 1: g_raw [B,N,4]; if
- *     g_raw_bf16 != NULL the same values are also written as bf16 rows of 64 (cols 4..63 zero),
- *     the A operand of the head dgrad/wgrad GEMMs).  distance carries no gradient.
+ *     (head_mode 0: g_rgb_in [B,N,3], g_density [B,N]) or the head outputs (head_mode 1: g_raw
+ *     [B,N,4] = dL/d raw).  density_to_weight: g_density = dL/d density (mode 0) or dL/d raw logit
+ *     (mode 1).  distance carries no gradient.
+ *   mip360_head_grad_pack: fp32 head-output gradient [M,n_valid] -> bf16 rows of 64 (zero padded) that
+ *     feed the head dgrad/wgrad GEMMs; act 2 folds the Sigmoid derivative y(1-y) of the saved head
+ *     output y (model.py:150-158), act 0 copies.
  * ------------------------------------------------------------------------------------------ */
 int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
@@ -132,12 +136,14 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in,
-                         float* g_density, float* g_raw, uint16_t* g_raw_bf16, mip360_stream_t stream);
+                         float* g_density, float* g_raw, mip360_stream_t stream);
 int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, float* weights, mip360_stream_t stream);
 int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, const float* g_w, float* g_density,
-                                 uint16_t* g_raw_bf16, mip360_stream_t stream);
+                                 mip360_stream_t stream);
+int mip360_head_grad_pack(const float* g, const float* y, long long M, int n_valid, int act, uint16_t* out_bf16,
+                          mip360_stream_t stream);
 /* intern/parameterization.py:5-8 incl. the in-place eps shifts one call observes (App. A4):
  * s = (1/(t+e) - 1/(near+e)) / (1/(far+e) - 1/(near+2e)); t_shift = t + e (may be NULL) */
 int mip360_t_to_s(const float* t_vals, const float* near, const float* far, int B, int K, float* s_vals,

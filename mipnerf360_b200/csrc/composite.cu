@@ -138,8 +138,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
                      int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
-                     float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw,
-                     uint16_t* __restrict__ g_raw_bf16) {
+                     float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw) {
   __shared__ CompositeSmem sm[CP_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CompositeSmem& s = sm[warp];
@@ -189,28 +188,10 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
           const float g_y0 = g_sigma * sigmoid_f(y0 + density_bias);
           const float g_y1 = r.w[c] * gr * cscale, g_y2 = r.w[c] * gg * cscale, g_y3 = r.w[c] * gb * cscale;
           if (g_raw) reinterpret_cast<float4*>(g_raw)[e] = make_float4(g_y0, g_y1, g_y2, g_y3);
-          if (g_raw_bf16) {
-            // gradient w.r.t. the head pre-activations (both heads end in a Sigmoid, model.py:150-158):
-            // recover the post-sigmoid colour values from the padded colour
-            const float y1 = (s.rgb[j * 3 + 0] + rgb_padding) / cscale;
-            const float y2 = (s.rgb[j * 3 + 1] + rgb_padding) / cscale;
-            const float y3 = (s.rgb[j * 3 + 2] + rgb_padding) / cscale;
-            uint4* row = reinterpret_cast<uint4*>(g_raw_bf16 + e * 64);
-            row[0] = make_uint4(pack_bf16x2(g_y0 * y0 * (1.f - y0), g_y1 * y1 * (1.f - y1)),
-                                pack_bf16x2(g_y2 * y2 * (1.f - y2), g_y3 * y3 * (1.f - y3)), 0u, 0u);
-#pragma unroll
-            for (int q = 1; q < 8; ++q) row[q] = make_uint4(0u, 0u, 0u, 0u);
-          }
         } else {
           if (density_mode == 1) {
             const float g_z = g_sigma * sigmoid_f(s.aux[j] + density_bias);
             if (g_density) g_density[e] = g_z;
-            if (g_raw_bf16) {
-              uint4* row = reinterpret_cast<uint4*>(g_raw_bf16 + e * 64);
-              row[0] = make_uint4(pack_bf16x2(g_z, 0.f), 0u, 0u, 0u);
-#pragma unroll
-              for (int q = 1; q < 8; ++q) row[q] = make_uint4(0u, 0u, 0u, 0u);
-            }
           } else if (g_density) {
             g_density[e] = g_sigma;
           }
@@ -253,6 +234,35 @@ s_to_t_kernel(const float* __restrict__ s_vals, const float* __restrict__ near, 
   t_vals[e] = 1.f / ((s * gf + (1.f - s) * gn) + G_EPS);
 }
 
+// Gradient w.r.t. the MLP head outputs -> bf16 rows of 64 for the head dgrad / wgrad GEMMs.
+// g [M, nv] fp32 is dL/dy; act 2 (Sigmoid head, model.py:150-158): dL/dz = g * y (1 - y) with the saved
+// head output y [M, nv]; act 0: dL/dz = g.  Columns nv..63 are zero.
+__global__ void __launch_bounds__(256)
+head_grad_pack_kernel(const float* __restrict__ g, const float* __restrict__ y, long long M, int nv, int act,
+                      uint16_t* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    z[i] = 0.f;
+    if (i < nv) {
+      const float gi = g[r * nv + i];
+      if (act == 2) {
+        const float yi = y[r * nv + i];
+        z[i] = gi * yi * (1.f - yi);
+      } else {
+        z[i] = gi;
+      }
+    }
+  }
+  uint4* row = reinterpret_cast<uint4*>(out + r * 64);
+  row[0] = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
+                      pack_bf16x2(z[6], z[7]));
+#pragma unroll
+  for (int q = 1; q < 8; ++q) row[q] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 static inline int ray_grid(int B, int warps) {
   long long b = ((long long)B + warps - 1) / warps;
   const long long cap = (long long)sm_count() * 16;
@@ -282,14 +292,14 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in, float* g_density,
-                         float* g_raw, uint16_t* g_raw_bf16, mip360_stream_t stream) {
+                         float* g_raw, mip360_stream_t stream) {
   MIP_REQUIRE(rgb_or_raw && t_vals && dirs, "composite_bwd: null pointer");
   MIP_REQUIRE(head_mode == 1 || density, "composite_bwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
       rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
-      g_w, g_rgb_in, g_density, g_raw, g_raw_bf16);
+      g_w, g_rgb_in, g_density, g_raw);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -308,14 +318,13 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
 
 int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, const float* g_w, float* g_density,
-                                 uint16_t* g_raw_bf16, mip360_stream_t stream) {
-  MIP_REQUIRE(density && t_vals && dirs && g_w, "density_to_weight_bwd: null pointer");
-  MIP_REQUIRE(g_density || g_raw_bf16, "density_to_weight_bwd: no output");
+                                 mip360_stream_t stream) {
+  MIP_REQUIRE(density && t_vals && dirs && g_w && g_density, "density_to_weight_bwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
       nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, g_w, nullptr,
-      g_density, nullptr, g_raw_bf16);
+      g_density, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -336,6 +345,17 @@ int mip360_s_to_t(const float* s_vals, const float* near, const float* far, int 
   if (B <= 0 || K <= 0) return MIP360_OK;
   const long long n = (long long)B * K;
   s_to_t_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s_vals, near, far, B, K, t_vals);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_head_grad_pack(const float* g, const float* y, long long M, int n_valid, int act, uint16_t* out_bf16,
+                          mip360_stream_t stream) {
+  MIP_REQUIRE(g && out_bf16, "head_grad_pack: null pointer");
+  MIP_REQUIRE(n_valid >= 1 && n_valid <= 8, "head_grad_pack: n_valid=%d outside [1,8]", n_valid);
+  MIP_REQUIRE(act == 0 || (act == 2 && y), "head_grad_pack: act=%d (0 or 2 with y)", act);
+  if (M <= 0) return MIP360_OK;
+  head_grad_pack_kernel<<<(int)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, y, M, n_valid, act, out_bf16);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -1,0 +1,195 @@
+"""Mirror of model.py: prop_net, nerf_net and mipNeRF360 with the reference's constructor arguments,
+forward signatures, return tuples, train/eval flag plumbing (App. A7) and state_dict keys,
+running on the fused sm_100a path:
+
+    level-0 sampling / resampling  ->  fused cast+contract+IPE (bf16 rows)  ->  tcgen05 MLP
+    ->  fused head activations + compositing  ->  t_to_s
+
+The fp32 nn.Linear parameters are the master weights (checkpoints round-trip with the reference);
+MLP arithmetic is bf16 x bf16 -> fp32 (mlp.py).  Inputs are never mutated (App. A4).
+"""
+import torch
+import torch.nn as nn
+
+from mipnerf360_b200 import mlp as _mlp
+from mipnerf360_b200 import ops
+from mipnerf360_b200.intern.encoding import PositionalEncoding, ViewdirectionEncoding
+from mipnerf360_b200.intern.ray import namedtuple_map
+from mipnerf360_b200.intern.utils import to8b
+
+
+def _kaiming_init(model):
+    """model.py:8-12."""
+    for module in model.modules():
+        if isinstance(module, nn.Linear):
+            nn.init.kaiming_uniform_(module.weight)
+
+
+def _encode(rays, t_vals, viewdirs_encoding, contract_mode):
+    """cast -> Gaussian -> contract -> IPE ++ view-direction encoding, straight to bf16 MLP rows
+    (model.py:82-88 / 169-176 without materialising means, covs or the [B,N,58] fp32 tensor)."""
+    vd = viewdirs_encoding(rays.viewdirs)
+    if vd.shape[-1] != 16:
+        raise ValueError("the fused encoder packs 16 view-direction features (viewdir_min_deg=0, viewdir_max_deg=4)")
+    return ops.cast_ipe(t_vals, rays.origins, rays.directions, rays.radii, vd, contract_mode=contract_mode,
+                        want_x=True)["x"]
+
+
+class prop_net(nn.Module):
+    def __init__(self, randomized=False, num_samples=128, hidden_proposal=256, density_bias=-1, viewdir_min_deg=0,
+                 viewdir_max_deg=4, device=torch.device("cuda")):
+        super().__init__()
+        self.randomized = randomized
+        self.num_samples = num_samples
+        self.hidden_proposal = hidden_proposal
+        self.density_bias = density_bias
+        self.viewdir_min_deg = viewdir_min_deg
+        self.viewdir_max_deg = viewdir_max_deg
+        self.device = device
+        self.contract_mode = ops.CONTRACT_REFERENCE
+
+        self.positional_encoding = PositionalEncoding()
+        self.viewdirs_encoding = ViewdirectionEncoding(self.viewdir_min_deg, self.viewdir_max_deg)
+        self.input_size = 21 * 2 + (self.viewdir_max_deg - self.viewdir_min_deg) * 2 * 2
+        self.density_activation = nn.Softplus()
+
+        # model.py:43-53 — same module order, so state_dict keys are prop_net.model.{0,2,4,6,8}.*
+        self.model = nn.Sequential(
+            nn.Linear(self.input_size, self.hidden_proposal), nn.ReLU(True),
+            nn.Linear(self.hidden_proposal, self.hidden_proposal), nn.ReLU(True),
+            nn.Linear(self.hidden_proposal, self.hidden_proposal), nn.ReLU(True),
+            nn.Linear(self.hidden_proposal, self.hidden_proposal), nn.Sigmoid(),
+            nn.Linear(self.hidden_proposal, 1))
+        _kaiming_init(self)
+        self.to(device)
+        self._packed = _mlp.pack_prop(self.model)
+
+    def density_to_weight(self, t_vals, density, dirs):
+        """model.py:59-78."""
+        return ops.density_to_weight(t_vals, density, dirs)
+
+    def forward(self, rays):
+        """model.py:80-94 -> (t_vals [B,N+1], weights [B,N])."""
+        B = rays.origins.shape[0]
+        t_vals = ops.level0_t_vals(rays.near, rays.far, self.num_samples, self.randomized)
+        x = _encode(rays, t_vals, self.viewdirs_encoding, self.contract_mode)
+        raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 1] logits
+        weights = ops.density_to_weight(t_vals, raw.view(B, self.num_samples), rays.directions, raw_logits=True,
+                                        density_bias=self.density_bias)
+        return t_vals, weights
+
+
+class nerf_net(nn.Module):
+    def __init__(self, randomized=False, num_samples=128, hidden_nerf=1024, density_bias=-1, rgb_padding=0.001,
+                 resample_padding=0.01, white_bkgd=False, viewdir_min_deg=0, viewdir_max_deg=4,
+                 device=torch.device("cuda")):
+        super().__init__()
+        self.randomized = randomized
+        self.num_samples = num_samples
+        self.hidden_nerf = hidden_nerf
+        self.density_bias = density_bias
+        self.rgb_padding = rgb_padding
+        self.resample_padding = resample_padding
+        self.white_bkgd = white_bkgd
+        self.viewdir_min_deg = viewdir_min_deg
+        self.viewdir_max_deg = viewdir_max_deg
+        self.device = device
+        self.contract_mode = ops.CONTRACT_REFERENCE
+
+        self.positional_encoding = PositionalEncoding()
+        self.viewdirs_encoding = ViewdirectionEncoding(self.viewdir_min_deg, self.viewdir_max_deg)
+        self.input_size = 21 * 2 + (self.viewdir_max_deg - self.viewdir_min_deg) * 2 * 2
+        self.density_activation = nn.Softplus()
+
+        # model.py:131-158 — keys nerf_net.model.{0,2,...,14}.*, final_density.0.*, final_color.0.*
+        layers = [nn.Linear(self.input_size, self.hidden_nerf), nn.ReLU(True)]
+        for _ in range(6):
+            layers += [nn.Linear(self.hidden_nerf, self.hidden_nerf), nn.ReLU(True)]
+        layers += [nn.Linear(self.hidden_nerf, self.hidden_nerf), nn.Sigmoid()]
+        self.model = nn.Sequential(*layers)
+        self.final_density = nn.Sequential(nn.Linear(self.hidden_nerf, 1), nn.Sigmoid())
+        self.final_color = nn.Sequential(nn.Linear(self.hidden_nerf, 3), nn.Sigmoid())
+        _kaiming_init(self)
+        self.to(device)
+        self._packed = _mlp.pack_nerf(self.model, self.final_density, self.final_color)
+
+    def forward(self, rays, t_vals, coarse_weights):
+        """model.py:163-200 -> (rgb [B,3], dist [B], acc [B], t_vals [B,N+1], weights [B,N], s_vals [B,N+1])."""
+        B = rays.origins.shape[0]
+        new_t = ops.resample(t_vals, coarse_weights, self.randomized, self.resample_padding)
+        N = new_t.shape[1] - 1
+        x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode)
+        raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 4] = (density head, colour head), post-sigmoid
+        comp_rgb, distance, acc, weights = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions,
+                                                               self.density_bias, self.rgb_padding, self.white_bkgd)
+        s_vals, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
+        # model.py:193-196: stashed for the distillation / regularisation losses; the reference's t_vals comes
+        # back shifted by +1e-6 because t_to_s -> g() adds eps in place (App. A4)
+        self.fine_weights = weights
+        self.t_vals = t_shift
+        self.s_vals = s_vals
+        return comp_rgb, distance, acc, self.t_vals, self.fine_weights, self.s_vals
+
+
+class mipNeRF360(nn.Module):
+    def __init__(self, randomized=False, num_samples=128, hidden_proposal=256, hidden_nerf=1024, density_bias=-1,
+                 rgb_padding=0.001, resample_padding=0.01, white_bkgd=False, viewdir_min_deg=0, viewdir_max_deg=4,
+                 device=torch.device("cuda")):
+        super().__init__()
+        self.randomized = randomized
+        self.num_samples = num_samples
+        self.hidden_proposal = hidden_proposal
+        self.hidden_nerf = hidden_nerf
+        self.density_bias = density_bias
+        self.rgb_padding = rgb_padding
+        self.resample_padding = resample_padding
+        self.white_bkgd = white_bkgd
+        self.viewdir_min_deg = viewdir_min_deg
+        self.viewdir_max_deg = viewdir_max_deg
+        self.device = device
+        self.init_randomized = randomized
+
+        self.prop_net = prop_net(randomized=self.randomized, num_samples=self.num_samples,
+                                 hidden_proposal=self.hidden_proposal, density_bias=self.density_bias,
+                                 viewdir_min_deg=self.viewdir_min_deg, viewdir_max_deg=self.viewdir_max_deg,
+                                 device=self.device)
+        self.nerf_net = nerf_net(randomized=self.randomized, num_samples=self.num_samples,
+                                 hidden_nerf=self.hidden_nerf, density_bias=self.density_bias,
+                                 rgb_padding=self.rgb_padding, resample_padding=self.resample_padding,
+                                 white_bkgd=self.white_bkgd, viewdir_min_deg=self.viewdir_min_deg,
+                                 viewdir_max_deg=self.viewdir_max_deg, device=self.device)
+        self.to(device)
+
+    def forward(self, rays):
+        """model.py:247-252."""
+        t_hat, w_hat = self.prop_net.forward(rays)
+        final_rgbs, final_dist, final_accs, _, _, _ = self.nerf_net.forward(rays, t_vals=t_hat, coarse_weights=w_hat)
+        return final_rgbs, final_dist, final_accs
+
+    def render_image(self, rays, height, width, chunks=4096):
+        """model.py:254-274: chunked inference.  Results stay on the device until the end (one D2H copy per
+        output instead of three per chunk plus a print)."""
+        length = rays[0].shape[0]
+        rgbs, dists, accs = [], [], []
+        with torch.no_grad():
+            for i in range(0, length, chunks):
+                chunk_rays = namedtuple_map(lambda r: r[i:i + chunks].to(self.device, non_blocking=True), rays)
+                rgb, distance, acc = self(chunk_rays)
+                rgbs.append(rgb)
+                dists.append(distance)
+                accs.append(acc)
+        rgbs = to8b(torch.cat(rgbs, dim=0).reshape(height, width, 3).cpu().numpy())
+        dists = torch.cat(dists, dim=0).reshape(height, width).cpu().numpy()
+        accs = torch.cat(accs, dim=0).reshape(height, width).cpu().numpy()
+        return rgbs, dists, accs
+
+    def train(self, mode=True):
+        """model.py:276-279."""
+        self.randomized = self.init_randomized
+        super().train(mode)
+        return self
+
+    def eval(self):
+        """model.py:281-283 (the sub-nets keep their own flags, App. A7)."""
+        self.randomized = False
+        return super().eval()

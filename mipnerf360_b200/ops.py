@@ -1,0 +1,476 @@
+"""Host-side operators over the C ABI (include/mip360_b200.h): output allocation, argument checking and
+torch.autograd.Function wrappers for the fwd/bwd kernel pairs.  torch is plumbing only (device
+memory, streams, autograd bookkeeping); every arithmetic step runs in libmip360_b200.so.
+
+Reference functions replaced (paths relative to the reference root) are cited per operator.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, check_cuda, f32c, ptr
+
+EPS32 = float(torch.finfo(torch.float32).eps)
+
+CONTRACT_REFERENCE, CONTRACT_PER_POINT, CONTRACT_NONE = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# K0 / K1
+# ------------------------------------------------------------------------------------------------
+def level0_t_vals(near, far, num_samples, randomized, t_rand=None):
+    """intern/ray.py:100-111.  near/far [B,1]; returns t_vals [B,N+1]."""
+    near, far = f32c(near), f32c(far)
+    check_cuda(near, far)
+    B = near.shape[0]
+    s_lin = torch.linspace(0.0, 1, num_samples + 1, device=near.device)
+    if randomized and t_rand is None:
+        t_rand = torch.rand(B, num_samples + 1, device=near.device)
+    if not randomized:
+        t_rand = None
+    else:
+        t_rand = f32c(t_rand)
+    t = _empty((B, num_samples + 1), near)
+    call("mip360_level0_t_vals", ptr(near), ptr(far), ptr(s_lin), ptr(t_rand), ptr(t), B, num_samples)
+    return t
+
+
+def viewdir_enc(viewdirs, min_deg=0, max_deg=4):
+    """intern/encoding.py:69-90."""
+    v = f32c(viewdirs)
+    check_cuda(v)
+    B = v.shape[0]
+    out = _empty((B, 4 * (max_deg - min_deg)), v)
+    call("mip360_viewdir_enc", ptr(v), B, int(min_deg), int(max_deg), ptr(out))
+    return out
+
+
+def frustum_norm_sq(t0, t1, t_stride, directions, B, N, out=None):
+    """Squared Frobenius norm the reference's contract() sees (intern/parameterization.py:25,75; App. A1).
+    Returns a device double scalar (accumulates into `out` if given)."""
+    if out is None:
+        out = torch.zeros(1, device=directions.device, dtype=torch.float64)
+    call("mip360_frustum_norm_sq", t0, t1, t_stride, ptr(directions), B, N, ptr(out))
+    return out
+
+
+def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=None, contract_mode=CONTRACT_REFERENCE,
+             add_origins=True, norm_sq=None, want_means=False, want_covs=False, want_enc=False, want_x=False):
+    """Fused cast -> Gaussian -> contract -> IPE (intern/parameterization.py:85-136, intern/encoding.py:33-61,
+    model.py:85-88).  Either t_vals [B,N+1] or separate t0, t1 [B,N].  Returns dict of requested outputs."""
+    directions, radii = f32c(directions), f32c(radii)
+    origins = f32c(origins) if origins is not None else None
+    if t_vals is not None:
+        t_vals = f32c(t_vals)
+        check_cuda(t_vals)
+        B, N = t_vals.shape[0], t_vals.shape[1] - 1
+        p0, p1, stride = t_vals.data_ptr(), t_vals.data_ptr() + 4, N + 1
+        keep = (t_vals,)
+    else:
+        t0, t1 = f32c(t0), f32c(t1)
+        check_cuda(t0, t1)
+        B, N = t0.shape
+        p0, p1, stride = t0.data_ptr(), t1.data_ptr(), N
+        keep = (t0, t1)
+    check_cuda(directions, radii, origins, vdir_enc)
+    dev = directions
+    if contract_mode == CONTRACT_REFERENCE and norm_sq is None:
+        norm_sq = frustum_norm_sq(p0, p1, stride, directions, B, N)
+    out = {}
+    means = _empty((B, N, 3), dev) if want_means else None
+    covs = _empty((B, N, 3, 3), dev) if want_covs else None
+    enc = _empty((B, N, 42), dev) if want_enc else None
+    x = _empty((B * N, 64), dev, torch.bfloat16) if want_x else None
+    if want_x and vdir_enc is None:
+        raise _lib.Mip360Error("cast_ipe: the bf16 MLP input needs vdir_enc")
+    call("mip360_cast_ipe", p0, p1, stride, ptr(origins), ptr(directions), ptr(vdir_enc), ptr(radii), ptr(norm_sq), B, N,
+         int(contract_mode), int(bool(add_origins)), ptr(means), ptr(covs), ptr(enc), ptr(x))
+    del keep
+    out.update(means=means, covs=covs, enc=enc, x=x, norm_sq=norm_sq)
+    return out
+
+
+def gaussian_to_xyz(d, t_mean, t_var, r_var):
+    """intern/parameterization.py:31-62 (diag=False)."""
+    d, t_mean, t_var, r_var = f32c(d), f32c(t_mean), f32c(t_var), f32c(r_var)
+    check_cuda(d, t_mean, t_var, r_var)
+    B, N = t_mean.shape
+    means, covs = _empty((B, N, 3), d), _empty((B, N, 3, 3), d)
+    call("mip360_gaussian_to_xyz", ptr(d), ptr(t_mean), ptr(t_var), ptr(r_var), B, N, ptr(means), ptr(covs))
+    return means, covs
+
+
+def sum_sq(x):
+    x = f32c(x)
+    check_cuda(x)
+    out = torch.zeros(1, device=x.device, dtype=torch.float64)
+    call("mip360_sum_sq", ptr(x), x.numel(), ptr(out))
+    return out
+
+
+def contract(x, norm_sq=None):
+    """intern/parameterization.py:23-29 (norm over the whole tensor, App. A1)."""
+    x = f32c(x)
+    check_cuda(x)
+    if norm_sq is None:
+        norm_sq = sum_sq(x)
+    y = torch.empty_like(x)
+    call("mip360_contract", ptr(x), x.numel(), ptr(norm_sq), ptr(y))
+    return y
+
+
+def gaussian_contract(mean, cov, norm_sq=None):
+    """intern/parameterization.py:64-83 with the closed-form Jacobian (App. A2/B1)."""
+    mean, cov = f32c(mean), f32c(cov)
+    check_cuda(mean, cov)
+    if norm_sq is None:
+        norm_sq = sum_sq(mean)
+    mo, co = torch.empty_like(mean), torch.empty_like(cov)
+    call("mip360_gaussian_contract", ptr(mean), ptr(cov), ptr(norm_sq), mean.numel() // 3, ptr(mo), ptr(co))
+    return mo, co
+
+
+def ipe(mean, cov):
+    """intern/encoding.py:33-61; cov None gives the plain positional encoding branch."""
+    mean = f32c(mean)
+    cov = f32c(cov) if cov is not None else None
+    check_cuda(mean, cov)
+    enc = _empty(mean.shape[:-1] + (42,), mean)
+    call("mip360_ipe", ptr(mean), ptr(cov), mean.numel() // 3, ptr(enc))
+    return enc
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+def blur_weights(weights, resample_padding):
+    """intern/ray.py:137-142."""
+    w = f32c(weights)
+    check_cuda(w)
+    out = torch.empty_like(w)
+    call("mip360_blur_weights", ptr(w), w.shape[0], w.shape[1], float(resample_padding), ptr(out))
+    return out
+
+
+def resample_cdf(weights):
+    """intern/ray.py:15-27."""
+    w = f32c(weights)
+    check_cuda(w)
+    B, N = w.shape
+    cdf = _empty((B, N + 1), w)
+    call("mip360_resample_cdf", ptr(w), B, N, ptr(cdf))
+    return cdf
+
+
+def resample_invert(bins, cdf, u, return_idx=False):
+    """intern/ray.py:41-56; u [B,M] or [M]."""
+    bins, cdf, u = f32c(bins), f32c(cdf), f32c(u)
+    check_cuda(bins, cdf, u)
+    B, K = cdf.shape
+    M = u.shape[-1]
+    stride = M if u.dim() == 2 and u.shape[0] == B else 0
+    samples = _empty((B, M), bins)
+    idx = _empty((B, M), bins, torch.int32) if return_idx else None
+    call("mip360_resample_invert", ptr(bins), ptr(cdf), ptr(u), stride, B, K - 1, M, ptr(samples), ptr(idx))
+    return (samples, idx) if return_idx else samples
+
+
+def pdf_u_base(num_samples, randomized, device):
+    """The per-stratum part of intern/ray.py:31-38, formed with the same torch ops as the reference so that
+    it is the same fp32 vector."""
+    if randomized:
+        s = 1 / num_samples
+        return torch.arange(num_samples, device=device) * s
+    return torch.linspace(0.0, 1.0 - EPS32, num_samples, device=device)
+
+
+def draw_jitter(B, num_samples, device):
+    """intern/ray.py:33: uniform_(0, 1/M - eps)."""
+    s = 1 / num_samples
+    return torch.empty(B, num_samples, device=device).uniform_(to=(s - EPS32))
+
+
+def resample(t_vals, weights, randomized, resample_padding, jitter=None, blur=True):
+    """The no_grad block of intern/ray.py:136-149 (blur=True) or intern/ray.py:12-57 alone (blur=False)."""
+    t_vals, weights = f32c(t_vals.detach()), f32c(weights.detach())
+    check_cuda(t_vals, weights)
+    B, N = weights.shape
+    u_base = f32c(pdf_u_base(N + 1, randomized, t_vals.device))
+    if randomized:
+        jitter = draw_jitter(B, N + 1, t_vals.device) if jitter is None else f32c(jitter)
+    else:
+        jitter = None
+    new_t = _empty((B, N + 1), t_vals)
+    call("mip360_resample", ptr(t_vals), ptr(weights), ptr(u_base), ptr(jitter), B, N, float(resample_padding),
+         int(bool(blur)), ptr(new_t))
+    return new_t
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    """intern/ray.py:155-191 (+ model.py:184-185 when head_mode=1)."""
+
+    @staticmethod
+    def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd):
+        B, N = t_vals.shape[0], t_vals.shape[1] - 1
+        comp, dist, acc = _empty((B, 3), t_vals), _empty((B,), t_vals), _empty((B,), t_vals)
+        w = _empty((B, N), t_vals)
+        call("mip360_composite_fwd", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
+             density_bias, rgb_padding, int(white_bkgd), ptr(comp), ptr(dist), ptr(acc), ptr(w))
+        ctx.save_for_backward(rgb_or_raw, density, t_vals, dirs)
+        ctx.cfg = (head_mode, density_bias, rgb_padding, int(white_bkgd))
+        ctx.mark_non_differentiable(dist)
+        return comp, dist, acc, w
+
+    @staticmethod
+    def backward(ctx, g_comp, g_dist, g_acc, g_w):
+        rgb_or_raw, density, t_vals, dirs = ctx.saved_tensors
+        head_mode, density_bias, rgb_padding, white = ctx.cfg
+        B, N = t_vals.shape[0], t_vals.shape[1] - 1
+        g_comp = f32c(g_comp) if g_comp is not None else None
+        g_acc = f32c(g_acc) if g_acc is not None else None
+        g_w = f32c(g_w) if g_w is not None else None
+        if head_mode == 1:
+            g_raw = torch.empty_like(rgb_or_raw)
+            g_rgb_in = g_density = None
+        else:
+            g_raw = None
+            g_rgb_in, g_density = torch.empty_like(rgb_or_raw), torch.empty_like(density)
+        call("mip360_composite_bwd", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
+             density_bias, rgb_padding, white, ptr(g_comp), ptr(g_acc), ptr(g_w), ptr(g_rgb_in), ptr(g_density),
+             ptr(g_raw))
+        if head_mode == 1:
+            return g_raw, None, None, None, None, None, None, None
+        return g_rgb_in, g_density, None, None, None, None, None, None
+
+
+def composite(rgb, density, t_vals, dirs, white_bkgd):
+    """volumetric_rendering(rgb [B,N,3], density [B,N,1] or [B,N], t_vals, dirs, white_bkgd)."""
+    rgb, t_vals, dirs = f32c(rgb), f32c(t_vals), f32c(dirs)
+    density = f32c(density.reshape(density.shape[0], density.shape[1]))
+    check_cuda(rgb, density, t_vals, dirs)
+    return _Composite.apply(rgb, density, t_vals, dirs, 0, 0.0, 0.0, bool(white_bkgd))
+
+
+def composite_heads(raw, t_vals, dirs, density_bias, rgb_padding, white_bkgd):
+    """model.py:184-186 fused: raw [B,N,4] = (density head, colour head) post-sigmoid outputs of the MLP."""
+    raw, t_vals, dirs = f32c(raw), f32c(t_vals), f32c(dirs)
+    check_cuda(raw, t_vals, dirs)
+    return _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd))
+
+
+class _DensityToWeight(torch.autograd.Function):
+    """model.py:59-78 (+ model.py:92 when density_mode=1)."""
+
+    @staticmethod
+    def forward(ctx, density, t_vals, dirs, density_mode, density_bias):
+        B, N = density.shape
+        w = _empty((B, N), density)
+        call("mip360_density_to_weight_fwd", ptr(density), ptr(t_vals), ptr(dirs), B, N, density_mode, density_bias,
+             ptr(w))
+        ctx.save_for_backward(density, t_vals, dirs)
+        ctx.cfg = (density_mode, density_bias)
+        return w
+
+    @staticmethod
+    def backward(ctx, g_w):
+        density, t_vals, dirs = ctx.saved_tensors
+        density_mode, density_bias = ctx.cfg
+        B, N = density.shape
+        g = torch.empty_like(density)
+        call("mip360_density_to_weight_bwd", ptr(density), ptr(t_vals), ptr(dirs), B, N, density_mode, density_bias,
+             ptr(f32c(g_w)), ptr(g))
+        return g, None, None, None, None
+
+
+def density_to_weight(t_vals, density, dirs, raw_logits=False, density_bias=0.0):
+    density = f32c(density.reshape(density.shape[0], density.shape[1]))
+    t_vals, dirs = f32c(t_vals), f32c(dirs)
+    check_cuda(density, t_vals, dirs)
+    return _DensityToWeight.apply(density, t_vals, dirs, 1 if raw_logits else 0, float(density_bias))
+
+
+def t_to_s(t_vals, near, far):
+    """intern/parameterization.py:5-8; returns (s_vals, t_vals + 1e-6) — the second is what the reference's
+    t_vals argument holds after the call (App. A4)."""
+    t_vals, near, far = f32c(t_vals), f32c(near), f32c(far)
+    check_cuda(t_vals, near, far)
+    B, K = t_vals.shape
+    s, ts = torch.empty_like(t_vals), torch.empty_like(t_vals)
+    call("mip360_t_to_s", ptr(t_vals), ptr(near), ptr(far), B, K, ptr(s), ptr(ts))
+    return s, ts
+
+
+def s_to_t(s_vals, near, far):
+    """intern/parameterization.py:10-13."""
+    s_vals, near, far = f32c(s_vals), f32c(near), f32c(far)
+    check_cuda(s_vals, near, far)
+    B, K = s_vals.shape
+    t = torch.empty_like(s_vals)
+    call("mip360_s_to_t", ptr(s_vals), ptr(near), ptr(far), B, K, ptr(t))
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K6
+# ------------------------------------------------------------------------------------------------
+def _partials(dev):
+    return torch.empty(_lib.load().mip360_partials_len(0), device=dev, dtype=torch.float64)
+
+
+class _Distortion(torch.autograd.Function):
+    """intern/regularization.py:3-19 (sum over the batch, both (i,j) orders, App. A9)."""
+
+    @staticmethod
+    def forward(ctx, s_vals, weights):
+        B, N = weights.shape
+        loss = _empty((), weights)
+        call("mip360_distortion_fwd", ptr(s_vals), ptr(weights), B, N, None, ptr(_partials(weights.device)), ptr(loss))
+        ctx.save_for_backward(s_vals, weights)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        s_vals, weights = ctx.saved_tensors
+        B, N = weights.shape
+        g_w = torch.empty_like(weights)
+        call("mip360_distortion_bwd", ptr(s_vals), ptr(weights), B, N, ptr(f32c(g)), ptr(g_w))
+        return None, g_w
+
+
+def distortion_loss(s_vals, weights):
+    s_vals, weights = f32c(s_vals), f32c(weights)
+    check_cuda(s_vals, weights)
+    return _Distortion.apply(s_vals.detach(), weights)
+
+
+def distortion_per_ray(s_vals, weights):
+    s_vals, weights = f32c(s_vals), f32c(weights)
+    check_cuda(s_vals, weights)
+    B, N = weights.shape
+    per_ray, loss = _empty((B,), weights), _empty((), weights)
+    call("mip360_distortion_fwd", ptr(s_vals), ptr(weights), B, N, ptr(per_ray), ptr(_partials(weights.device)),
+         ptr(loss))
+    return per_ray
+
+
+def bounds_per_ray(t_fine, w_fine, t_coarse):
+    t_fine, w_fine, t_coarse = f32c(t_fine.detach()), f32c(w_fine.detach()), f32c(t_coarse.detach())
+    check_cuda(t_fine, w_fine, t_coarse)
+    B, N = w_fine.shape
+    b = _empty((B, N), w_fine)
+    call("mip360_bounds_per_ray", ptr(t_fine), ptr(w_fine), ptr(t_coarse), B, N, ptr(b))
+    return b
+
+
+def bounds_total(b_per_ray, out=None):
+    """Column sums over rays (fp64): the value intern/distillation.py:25-29 broadcasts to every ray (App. A6)."""
+    B, N = b_per_ray.shape
+    if out is None:
+        out = torch.zeros(N, device=b_per_ray.device, dtype=torch.float64)
+    call("mip360_bounds_reduce", ptr(b_per_ray), B, N, ptr(out))
+    return out
+
+
+class _Interlevel(torch.autograd.Function):
+    """intern/distillation.py:35-51 given detached bounds."""
+
+    @staticmethod
+    def forward(ctx, w_hat, b_per_ray, bound_total, bound_mode, batch_div):
+        B, N = w_hat.shape
+        loss = _empty((), w_hat)
+        call("mip360_interlevel_fwd", ptr(w_hat), ptr(b_per_ray), ptr(bound_total), B, N, bound_mode, batch_div,
+             ptr(_partials(w_hat.device)), ptr(loss))
+        ctx.save_for_backward(w_hat, b_per_ray, bound_total)
+        ctx.cfg = (bound_mode, batch_div)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        w_hat, b_per_ray, bound_total = ctx.saved_tensors
+        bound_mode, batch_div = ctx.cfg
+        B, N = w_hat.shape
+        g_w = torch.empty_like(w_hat)
+        call("mip360_interlevel_bwd", ptr(w_hat), ptr(b_per_ray), ptr(bound_total), B, N, bound_mode, batch_div,
+             ptr(f32c(g)), ptr(g_w))
+        return g_w, None, None, None, None
+
+
+def interlevel_loss(w_hat, b_per_ray=None, bound_total=None, per_ray_bounds=False, batch_div=None):
+    w_hat = f32c(w_hat)
+    check_cuda(w_hat)
+    if batch_div is None:
+        batch_div = float(w_hat.shape[0])
+    return _Interlevel.apply(w_hat, b_per_ray, bound_total, 1 if per_ray_bounds else 0, float(batch_div))
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+def cast_weight(W, n_pad=None, k_pad=None, transposed=True):
+    """fp32 [N,K] -> bf16 [Npad,Kpad] and its transpose [Kpad,Npad] (zero padded)."""
+    W = f32c(W.detach())
+    check_cuda(W)
+    N, K = W.shape
+    n_pad, k_pad = n_pad or _pad64(N), k_pad or _pad64(K)
+    Wb = torch.empty((n_pad, k_pad), device=W.device, dtype=torch.bfloat16)
+    Wt = torch.empty((k_pad, n_pad), device=W.device, dtype=torch.bfloat16) if transposed else None
+    call("mip360_cast_weight", ptr(W), N, K, n_pad, k_pad, ptr(Wb), ptr(Wt))
+    return Wb, Wt
+
+
+def linear_fwd(x, Wb, bias, act, out_f32_cols=0, want_bf16=True):
+    """Y = act(x Wb^T + bias): x bf16 [M,K], Wb bf16 [N,K], bias fp32 [N]."""
+    M, K = x.shape
+    N = Wb.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    yf = torch.empty((M, out_f32_cols), device=x.device, dtype=torch.float32) if out_f32_cols else None
+    call("mip360_linear_fwd", ptr(x), ptr(Wb), ptr(bias), M, N, K, act, ptr(y), ptr(yf), out_f32_cols)
+    return y, yf
+
+
+def linear_dgrad(dY, Wt, y_prev, act, out=None):
+    """dX = (dY Wt^T) .* act'(y_prev): dY bf16 [M,N], Wt bf16 [K,N], y_prev bf16 [M,K]."""
+    M, N = dY.shape
+    K = Wt.shape[0]
+    dX = out if out is not None else torch.empty((M, K), device=dY.device, dtype=torch.bfloat16)
+    call("mip360_linear_dgrad", ptr(dY), ptr(Wt), ptr(y_prev), M, N, K, act, ptr(dX))
+    return dX
+
+
+def linear_wgrad(dY, x, dW=None, db=None, want_db=True):
+    """dW[N,K] += dY^T x, db[N] += colsum(dY): dY bf16 [M,N], x bf16 [M,K]; fp32 outputs (zeroed if new)."""
+    M, N = dY.shape
+    K = x.shape[1]
+    if dW is None:
+        dW = torch.zeros((N, K), device=dY.device, dtype=torch.float32)
+    if db is None and want_db:
+        db = torch.zeros((N,), device=dY.device, dtype=torch.float32)
+    call("mip360_linear_wgrad", ptr(dY), ptr(x), M, N, K, ptr(dW), ptr(db))
+    return dW, db
+
+
+def head_grad_pack(g, y, act):
+    """fp32 head gradient [M,nv] -> bf16 [M,64] rows with the head activation derivative folded in."""
+    g = f32c(g)
+    M, nv = g.shape
+    out = torch.empty((M, 64), device=g.device, dtype=torch.bfloat16)
+    call("mip360_head_grad_pack", ptr(g), ptr(y), M, nv, act, ptr(out))
+    return out
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    call("mip360_adamw", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), int(step))
