@@ -98,9 +98,22 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# When set to a list, every call is bracketed by CUDA events on the launching stream and
+# (name, int args, start, end) is appended: bench.py reads per-kernel durations from it.
+PROFILE = None
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if PROFILE is None:
+        rc = getattr(lib, name)(*args, stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        PROFILE.append((name, tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and a < (1 << 31)),
+                        e0, e1))
     if rc != 0:
         raise Mip360Error(f"{name} failed ({rc}): {lib.mip360_last_error().decode()}")
 

@@ -36,6 +36,10 @@ class PackedMLP:
         self._key = None
         self._packed = None
 
+    def invalidate(self):
+        """Force a re-cast of the bf16 operands (for optimisers that update the weights behind autograd's back)."""
+        self._key = None
+
     def params(self):
         ps = []
         for lin, _ in self.trunk:
@@ -74,7 +78,7 @@ class _MLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, mlp, *params):
         layers, (Wh, Wht, bh) = mlp.packed()
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside forward(); autograd tells us here
         acts = [a for _, a in mlp.trunk]
         saved = [x]
         h = x

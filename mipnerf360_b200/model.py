@@ -9,6 +9,7 @@ The fp32 nn.Linear parameters are the master weights (checkpoints round-trip wit
 MLP arithmetic is bf16 x bf16 -> fp32 (mlp.py).  Inputs are never mutated (App. A4).
 """
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from mipnerf360_b200 import mlp as _mlp
@@ -16,6 +17,11 @@ from mipnerf360_b200 import ops
 from mipnerf360_b200.intern.encoding import PositionalEncoding, ViewdirectionEncoding
 from mipnerf360_b200.intern.ray import namedtuple_map
 from mipnerf360_b200.intern.utils import to8b
+
+
+# With torch.distributed initialised, all-reduce the batch-coupled contraction norm so that a ray-sharded
+# forward equals the unsharded one.  Rendering shards set this to False (independent chunks).
+SYNC_BATCH_STATS = True
 
 
 def _kaiming_init(model):
@@ -31,8 +37,16 @@ def _encode(rays, t_vals, viewdirs_encoding, contract_mode):
     vd = viewdirs_encoding(rays.viewdirs)
     if vd.shape[-1] != 16:
         raise ValueError("the fused encoder packs 16 view-direction features (viewdir_min_deg=0, viewdir_max_deg=4)")
+    norm_sq = None
+    if contract_mode == ops.CONTRACT_REFERENCE and SYNC_BATCH_STATS and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size() > 1:
+        # ray-sharded run: the reference's contraction norm is over the WHOLE batch (App. A1), i.e. all ranks
+        t = ops.f32c(t_vals)
+        B, N = t.shape[0], t.shape[1] - 1
+        norm_sq = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, ops.f32c(rays.directions), B, N)
+        dist.all_reduce(norm_sq, op=dist.ReduceOp.SUM)
     return ops.cast_ipe(t_vals, rays.origins, rays.directions, rays.radii, vd, contract_mode=contract_mode,
-                        want_x=True)["x"]
+                        norm_sq=norm_sq, want_x=True)["x"]
 
 
 class prop_net(nn.Module):

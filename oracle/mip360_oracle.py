@@ -186,7 +186,7 @@ def pdf_to_cdf(weights):
     wsum = wsum + padding
     pdf = w / wsum
     cdf = torch.clamp(torch.cumsum(pdf[..., :-1], dim=-1), max=1)
-    zeros = torch.zeros_like(cdf[..., :1])
+    zeros = torch.zeros(cdf.shape[:-1] + (1,), dtype=cdf.dtype, device=cdf.device)  # N = 1: cdf is empty here
     return torch.cat([zeros, cdf, zeros + 1], dim=-1)
 
 

@@ -169,7 +169,9 @@ def test_cast_ipe_vs_oracle(ops, B, N):
 
 
 def test_cast_ipe_modes_and_empty(ops):
-    rays_c, rays = make_rays(16, 3, far=1e3)
+    # far = 20 keeps |mean| <= ~60: J cov J^T cancels from O(1/m) entries down to the O(1/m^2) radial
+    # eigenvalue, so fp32 (kernel AND reference) carries a relative error ~ 2m*eps; the tolerance reflects it
+    rays_c, rays = make_rays(16, 3, far=20.0)
     N = 8
     t_c = O.level0_t_vals(rays_c.near, rays_c.far, N, False)
     t = t_c.to(DEV)
@@ -183,7 +185,7 @@ def test_cast_ipe_modes_and_empty(ops):
     J = O.contract_jacobian(mean)
     cov_c = J @ cov @ J.transpose(-1, -2)
     close(out["means"], mean_c.float(), atol=1e-6)
-    cov_close(out["covs"], cov_c.float())
+    cov_close(out["covs"], cov_c.float(), rel=1e-4)
     assert (n > 1).any() and (n <= 1).any()
     # no contraction
     out = ops.cast_ipe(t, rays.origins, rays.directions, rays.radii, contract_mode=ops.CONTRACT_NONE,
