@@ -32,13 +32,18 @@ struct LinearCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp one 4 KB [32 rows x 64 cols] bf16 box for the TMA store, and a second
+  // region of the same size that holds the saved-activation box (dgrad) or, shared by all warps, the bias
+  // tile of the two accumulator stages (fwd)
+  static constexpr int EPI_BOX_BYTES = 32 * 64 * 2;
+  static constexpr int EPI_BYTES = 2 * 4 * EPI_BOX_BYTES;
+  static constexpr int BAR_BYTES = 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
 struct LinearParams {
   const float* bias;       // [N] (EPI_FWD) or null
-  const uint16_t* yprev;   // [M, N] saved activation output (EPI_DGRAD)
-  uint16_t* out_bf16;      // [M, N] or null
+  uint16_t* out_bf16;      // [M, N] or null (then only out_f32 is written)
   float* out_f32;          // [M, n_valid] or null
   int M, N, K, act, n_valid;
 };
@@ -48,20 +53,38 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
   return x;
 }
+__device__ __forceinline__ float act_bwd(float y, int act) {
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_y,
               const LinearParams p) {
   using Cfg = LinearCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto y_bar = [&](int q) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + q); };   // 2*6+4+4 = 20 barriers max
+  const uint32_t tmem_slot = bar_base + 8u * 20;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
@@ -77,9 +100,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);
     }
+    for (int q = 0; q < 4; ++q) mbar_init(y_bar(q), 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
+    if (EPI == EPI_DGRAD) prefetch_tmap(&tmap_y);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -135,79 +161,106 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to warp with (warp % 4) == q =====
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to the warp with (warp % 4) == q =====
+    // accumulator -> registers -> (bias, activation | activation derivative) -> bf16 -> swizzled smem box
+    // [32 rows x 64 cols] -> TMA store.  Each warp owns its boxes, so only __syncwarp is needed.
     const int q = warp & 3;
-    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t out_box = epi_base + q * Cfg::EPI_BOX_BYTES;
+    const uint32_t y_box = epi_base + 4 * Cfg::EPI_BOX_BYTES + q * Cfg::EPI_BOX_BYTES;  // dgrad only
+    const uint32_t bias_smem = epi_base + 4 * Cfg::EPI_BOX_BYTES;                        // fwd only: 2 x BN floats
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const bool tma_out = p.out_bf16 != nullptr;
+    uint32_t acc = 0, acc_phase = 0, y_phase = 0;
+    if (EPI == EPI_DGRAD && lane == 0 && (int)blockIdx.x < total_tiles) {
+      const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
+      mbar_arrive_expect_tx(y_bar(q), Cfg::EPI_BOX_BYTES);
+      tma_load_2d(y_box, &tmap_y, y_bar(q), n0, m0 + q * 32);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      if (EPI == EPI_FWD) {
+        // bias tile of this accumulator stage into shared memory (read back as broadcasts)
+        const int t = threadIdx.x - 64;  // 0..127
+        for (int i = t; i < BN; i += 128)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + (acc * BN + i) * 4u), "f"(__ldg(p.bias + n0 + i)) : "memory");
+        epi_bar_sync();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        float x[32];
-        if (EPI == EPI_FWD) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+      for (int jj = 0; jj < BN / 64; ++jj) {
+        uint32_t packed[32];  // 64 bf16 of this lane's row
+        uint4 yv[8];
+        if (EPI == EPI_DGRAD) {
+          mbar_wait(y_bar(q), y_phase);
+          y_phase ^= 1u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(b4 + i);
-            x[4 * i + 0] = act_fwd(__uint_as_float(v[4 * i + 0]) + bb.x, p.act);
-            x[4 * i + 1] = act_fwd(__uint_as_float(v[4 * i + 1]) + bb.y, p.act);
-            x[4 * i + 2] = act_fwd(__uint_as_float(v[4 * i + 2]) + bb.z, p.act);
-            x[4 * i + 3] = act_fwd(__uint_as_float(v[4 * i + 3]) + bb.w, p.act);
-          }
-        } else {
-          // dX = acc .* act'(y), y = saved output of the layer whose input gradient this is
-          uint4 yv[4];
-          if (row_ok) {
-            const uint4* y4 = reinterpret_cast<const uint4*>(p.yprev + (size_t)row * p.N + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) yv[i] = __ldg(y4 + i);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) yv[i] = make_uint4(0, 0, 0, 0);
-          }
-          const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
-            float d_lo, d_hi;
-            if (p.act == ACT_RELU) {
-              d_lo = y_lo > 0.f ? 1.f : 0.f;
-              d_hi = y_hi > 0.f ? 1.f : 0.f;
-            } else if (p.act == ACT_SIGMOID) {
-              d_lo = y_lo * (1.f - y_lo);
-              d_hi = y_hi * (1.f - y_hi);
-            } else {
-              d_lo = d_hi = 1.f;
+          for (int c = 0; c < 8; ++c) yv[c] = ld_shared_v4(y_box + row_off + ((c ^ sw) << 4));
+          __syncwarp();
+          if (lane == 0) {
+            // prefetch the next saved-activation box (next column chunk, or the first one of the next tile)
+            int nt = tile, nj = jj + 1;
+            if (nj == BN / 64) { nj = 0; nt = tile + gridDim.x; }
+            if (nt < total_tiles) {
+              const int nm0 = (nt / tiles_n) * BM, nn0 = (nt % tiles_n) * BN;
+              mbar_arrive_expect_tx(y_bar(q), Cfg::EPI_BOX_BYTES);
+              tma_load_2d(y_box, &tmap_y, y_bar(q), nn0 + nj * 64, nm0 + q * 32);
             }
-            x[2 * i] = __uint_as_float(v[2 * i]) * d_lo;
-            x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * d_hi;
           }
         }
-        if (row_ok) {
-          if (p.out_bf16) {
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.N + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(x[8 * i], x[8 * i + 1]), pack_bf16x2(x[8 * i + 2], x[8 * i + 3]),
-                                 pack_bf16x2(x[8 * i + 4], x[8 * i + 5]), pack_bf16x2(x[8 * i + 6], x[8 * i + 7]));
-          }
-          if (p.out_f32 && col0 == 0) {
-            float* o = p.out_f32 + (size_t)row * p.n_valid;
-            if (p.n_valid == 4) {
-              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-            } else {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
+          tmem_ld_wait();
+          float x[32];
+          if (EPI == EPI_FWD) {
+            const uint32_t bsm = bias_smem + (acc * BN + jj * 64 + h * 32) * 4u;
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i < p.n_valid) o[i] = x[i];
+            for (int i = 0; i < 8; ++i) {
+              const uint4 bb = ld_shared_v4(bsm + 16u * i);
+              x[4 * i + 0] = act_fwd(__uint_as_float(v[4 * i + 0]) + __uint_as_float(bb.x), p.act);
+              x[4 * i + 1] = act_fwd(__uint_as_float(v[4 * i + 1]) + __uint_as_float(bb.y), p.act);
+              x[4 * i + 2] = act_fwd(__uint_as_float(v[4 * i + 2]) + __uint_as_float(bb.z), p.act);
+              x[4 * i + 3] = act_fwd(__uint_as_float(v[4 * i + 3]) + __uint_as_float(bb.w), p.act);
             }
+            if (p.out_f32 && jj == 0 && h == 0 && n0 == 0 && row < p.M) {
+              float* o = p.out_f32 + (size_t)row * p.n_valid;
+              if (p.n_valid == 4) {
+                *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (i < p.n_valid) o[i] = x[i];
+              }
+            }
+          } else {
+            const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yv[4 * h]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
+              x[2 * i] = __uint_as_float(v[2 * i]) * act_bwd(y_lo, p.act);
+              x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * act_bwd(y_hi, p.act);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[16 * h + i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+        }
+        if (tma_out) {
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has finished reading out_box
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(out_box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2],
+                         packed[4 * c + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, out_box, n0 + jj * 64, m0 + q * 32);
+            tma_store_commit();
           }
         }
       }
@@ -216,6 +269,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -448,29 +502,35 @@ static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long lon
 }
 
 template <int BN, int EPI>
-static int launch_linear(const uint16_t* A, const uint16_t* Bw, const LinearParams& p, cudaStream_t stream) {
+static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
+                         cudaStream_t stream) {
   using Cfg = LinearCfg<BN>;
   static bool configured = false;
   if (!configured) {
     MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tout, ty;
   int rc;
   if ((rc = make_tmap(&ta, A, p.M, p.K, BM)) != MIP360_OK) return rc;
   if ((rc = make_tmap(&tb, Bw, p.N, p.K, BN)) != MIP360_OK) return rc;
+  tout = ta;
+  ty = ta;
+  if (p.out_bf16 && (rc = make_tmap(&tout, p.out_bf16, p.M, p.N, 32)) != MIP360_OK) return rc;
+  if (EPI == EPI_DGRAD && (rc = make_tmap(&ty, yprev, p.M, p.N, 32)) != MIP360_OK) return rc;
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  linear_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
 
 template <int EPI>
-static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const LinearParams& p, cudaStream_t stream) {
-  if (p.N % 256 == 0) return launch_linear<256, EPI>(A, Bw, p, stream);
-  if (p.N == 128) return launch_linear<128, EPI>(A, Bw, p, stream);
-  if (p.N == 64) return launch_linear<64, EPI>(A, Bw, p, stream);
+static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
+                           cudaStream_t stream) {
+  if (p.N % 256 == 0) return launch_linear<256, EPI>(A, Bw, yprev, p, stream);
+  if (p.N == 128) return launch_linear<128, EPI>(A, Bw, yprev, p, stream);
+  if (p.N == 64) return launch_linear<64, EPI>(A, Bw, yprev, p, stream);
   set_error("linear: N=%d not supported (need 64, 128 or a multiple of 256)", p.N);
   return MIP360_ERR_UNSUPPORTED;
 }
@@ -512,18 +572,18 @@ int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, i
   MIP_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "linear_fwd: bad shape M=%d N=%d K=%d (K %% 64 != 0?)", M, N, K);
   MIP_REQUIRE(!out_f32 || (n_valid >= 1 && n_valid <= 8), "linear_fwd: n_valid=%d outside [1,8]", n_valid);
   MIP_REQUIRE(act >= 0 && act <= 2, "linear_fwd: act=%d", act);
-  LinearParams p{bias, nullptr, out_bf16, out_f32, M, N, K, act, n_valid};
-  return dispatch_linear<EPI_FWD>(X, W, p, (cudaStream_t)stream);
+  LinearParams p{bias, out_bf16, out_f32, M, N, K, act, n_valid};
+  return dispatch_linear<EPI_FWD>(X, W, nullptr, p, (cudaStream_t)stream);
 }
 
 int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,
                         uint16_t* dX, mip360_stream_t stream) {
   // GEMM view: out[M, K] = dY[M, N] * Wt[K, N]^T : reduction over N, output width K
   MIP_REQUIRE(dY && Wt && dX, "linear_dgrad: null pointer");
-  MIP_REQUIRE(act == ACT_NONE || Yprev, "linear_dgrad: activation derivative needs Yprev");
+  MIP_REQUIRE(Yprev, "linear_dgrad: the saved activation output Yprev is required");
   MIP_REQUIRE(M > 0 && N > 0 && K > 0 && N % BK == 0, "linear_dgrad: bad shape M=%d N=%d K=%d (N %% 64 != 0?)", M, N, K);
-  LinearParams p{nullptr, Yprev, dX, nullptr, M, /*N=*/K, /*K=*/N, act, 0};
-  return dispatch_linear<EPI_DGRAD>(dY, Wt, p, (cudaStream_t)stream);
+  LinearParams p{nullptr, dX, nullptr, M, /*N=*/K, /*K=*/N, act, 0};
+  return dispatch_linear<EPI_DGRAD>(dY, Wt, Yprev, p, (cudaStream_t)stream);
 }
 
 int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int K, float* dW, float* db,

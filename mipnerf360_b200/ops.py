@@ -80,6 +80,11 @@ def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=N
         keep = (t0, t1)
     check_cuda(directions, radii, origins, vdir_enc)
     dev = directions
+    if B == 0:
+        return dict(means=_empty((0, N, 3), dev) if want_means else None,
+                    covs=_empty((0, N, 3, 3), dev) if want_covs else None,
+                    enc=_empty((0, N, 42), dev) if want_enc else None,
+                    x=_empty((0, 64), dev, torch.bfloat16) if want_x else None, norm_sq=norm_sq)
     if contract_mode == CONTRACT_REFERENCE and norm_sq is None:
         norm_sq = frustum_norm_sq(p0, p1, stride, directions, B, N)
     out = {}

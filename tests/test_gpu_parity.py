@@ -528,8 +528,9 @@ def test_default_model_vs_oracle():
         assert rel < 1e-1, (k, rel)
     print("worst relative gradient error (bf16 MLP vs fp32 oracle):", worst)
     # plain forward through the public entry point, eval flag plumbing (App. A7)
-    m.eval()
-    assert m.randomized is False and m.prop_net.randomized is True
+    m.eval()  # eval() -> nn.Module.eval() -> self.train(False) -> resets the flag: still True afterwards (App. A7)
+    assert m.randomized is True and m.prop_net.randomized is True and m.nerf_net.randomized is True
+    assert not m.training
     m.train()
     out = m(rays)
     assert out[0].shape == (B, 3) and out[1].shape == (B,) and out[2].shape == (B,)
