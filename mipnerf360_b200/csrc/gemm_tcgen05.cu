@@ -23,7 +23,7 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
 enum { EPI_FWD = 0, EPI_DGRAD = 1 };
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_SIGMOID_FAST = 3 /* internal: bf16-only outputs */ };
 
 template <int BN>
 struct LinearCfg {
@@ -36,8 +36,8 @@ struct LinearCfg {
   // region of the same size that holds the saved-activation box (dgrad) or, shared by all warps, the bias
   // tile of the two accumulator stages (fwd)
   static constexpr int EPI_BOX_BYTES = 32 * 64 * 2;
-  static constexpr int EPI_BYTES = 2 * 4 * EPI_BOX_BYTES;
-  static constexpr int BAR_BYTES = 128;
+  static constexpr int EPI_BYTES = 2 * 4 * EPI_BOX_BYTES + 1024 /* bias tile: up to 256 floats */;
+  static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
@@ -48,15 +48,51 @@ struct LinearParams {
   int M, N, K, act, n_valid;
 };
 
-__device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == ACT_RELU) return fmaxf(x, 0.f);
-  if (act == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
-  return x;
+// 32 accumulator columns of one row: + bias (broadcast reads from shared memory), activation
+template <int ACT>
+__device__ __forceinline__ void fwd_math(const uint32_t (&v)[32], uint32_t bias_addr, float (&x)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 bb;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bb.x), "=r"(bb.y), "=r"(bb.z), "=r"(bb.w) : "r"(bias_addr + 16u * i));
+    const float z[4] = {__uint_as_float(v[4 * i + 0]) + __uint_as_float(bb.x), __uint_as_float(v[4 * i + 1]) + __uint_as_float(bb.y),
+                        __uint_as_float(v[4 * i + 2]) + __uint_as_float(bb.z), __uint_as_float(v[4 * i + 3]) + __uint_as_float(bb.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r;
+      if (ACT == ACT_RELU) {
+        r = fmaxf(z[e], 0.f);
+      } else if (ACT == ACT_SIGMOID) {
+        r = __fdividef(1.f, 1.f + __expf(-z[e]));
+      } else if (ACT == ACT_SIGMOID_FAST) {
+        // sigmoid(z) = 0.5 tanh(z/2) + 0.5: one MUFU op; |error| ~ 2.4e-4, an eighth of the bf16 rounding of the output
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z[e]));
+        r = fmaf(0.5f, t, 0.5f);
+      } else {
+        r = z[e];
+      }
+      x[4 * i + e] = r;
+    }
+  }
 }
-__device__ __forceinline__ float act_bwd(float y, int act) {
-  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == ACT_SIGMOID) return y * (1.f - y);
-  return 1.f;
+// dX = acc .* act'(y) with y the saved bf16 output of the layer (16 packed pairs)
+template <int ACT>
+__device__ __forceinline__ void bwd_math(const uint32_t (&v)[32], const uint32_t* yw, float (&x)[32]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
+    float d_lo = 1.f, d_hi = 1.f;
+    if (ACT == ACT_RELU) {
+      d_lo = y_lo > 0.f ? 1.f : 0.f;
+      d_hi = y_hi > 0.f ? 1.f : 0.f;
+    } else if (ACT == ACT_SIGMOID) {
+      d_lo = y_lo * (1.f - y_lo);
+      d_hi = y_hi * (1.f - y_hi);
+    }
+    x[2 * i] = __uint_as_float(v[2 * i]) * d_lo;
+    x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * d_hi;
+  }
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -83,8 +119,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  auto y_bar = [&](int q) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + q); };   // 2*6+4+4 = 20 barriers max
-  const uint32_t tmem_slot = bar_base + 8u * 20;
+  auto y_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + i); };   // 2*6+4+8 = 24 barriers max
+  const uint32_t tmem_slot = bar_base + 8u * 24;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
@@ -100,7 +136,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);
     }
-    for (int q = 0; q < 4; ++q) mbar_init(y_bar(q), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(y_bar(i), 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -163,53 +199,49 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   } else {
     // ===== epilogue warps: TMEM lanes [32q, 32q+32) belong to the warp with (warp % 4) == q =====
     // accumulator -> registers -> (bias, activation | activation derivative) -> bf16 -> swizzled smem box
-    // [32 rows x 64 cols] -> TMA store.  Each warp owns its boxes, so only __syncwarp is needed.
+    // [32 rows x 64 cols] -> TMA store.  Each warp owns two boxes and alternates between them, so a store is
+    // still reading one box while the next chunk is being produced; only __syncwarp is needed.
+    // dgrad: the box first receives the saved-activation tile by TMA (prefetched one chunk ahead), each lane
+    // reads its own row, and the result is written back in place before the box is stored.
     const int q = warp & 3;
-    const uint32_t out_box = epi_base + q * Cfg::EPI_BOX_BYTES;
-    const uint32_t y_box = epi_base + 4 * Cfg::EPI_BOX_BYTES + q * Cfg::EPI_BOX_BYTES;  // dgrad only
-    const uint32_t bias_smem = epi_base + 4 * Cfg::EPI_BOX_BYTES;                        // fwd only: 2 x BN floats
+    const uint32_t box0 = epi_base + q * 2 * Cfg::EPI_BOX_BYTES;
+    const uint32_t bias_smem = epi_base + 8 * Cfg::EPI_BOX_BYTES;  // fwd: BN floats, shared by the 4 warps
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const bool tma_out = p.out_bf16 != nullptr;
-    uint32_t acc = 0, acc_phase = 0, y_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, cnt = 0;
+    int bias_n0 = -1;
     if (EPI == EPI_DGRAD && lane == 0 && (int)blockIdx.x < total_tiles) {
       const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
-      mbar_arrive_expect_tx(y_bar(q), Cfg::EPI_BOX_BYTES);
-      tma_load_2d(y_box, &tmap_y, y_bar(q), n0, m0 + q * 32);
+      mbar_arrive_expect_tx(y_bar(2 * q), Cfg::EPI_BOX_BYTES);
+      tma_load_2d(box0, &tmap_y, y_bar(2 * q), n0, m0 + q * 32);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
-      if (EPI == EPI_FWD) {
-        // bias tile of this accumulator stage into shared memory (read back as broadcasts)
-        const int t = threadIdx.x - 64;  // 0..127
+      if (EPI == EPI_FWD && n0 != bias_n0) {
+        // bias tile into shared memory (read back as broadcasts).  With gridDim.x a multiple of the number
+        // of column tiles every CTA keeps the same column block, so this runs once per kernel.
+        if (bias_n0 >= 0) epi_bar_sync();  // everyone has finished reading the previous tile's bias
+        const int t = threadIdx.x - 64;    // 0..127
         for (int i = t; i < BN; i += 128)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + (acc * BN + i) * 4u), "f"(__ldg(p.bias + n0 + i)) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + i * 4u), "f"(__ldg(p.bias + n0 + i)) : "memory");
         epi_bar_sync();
+        bias_n0 = n0;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int jj = 0; jj < BN / 64; ++jj) {
+      for (int jj = 0; jj < BN / 64; ++jj, ++cnt) {
+        const uint32_t b = cnt & 1u;
+        const uint32_t box = box0 + b * Cfg::EPI_BOX_BYTES;
         uint32_t packed[32];  // 64 bf16 of this lane's row
         uint4 yv[8];
         if (EPI == EPI_DGRAD) {
-          mbar_wait(y_bar(q), y_phase);
-          y_phase ^= 1u;
+          mbar_wait(y_bar(2 * q + b), (cnt >> 1) & 1u);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) yv[c] = ld_shared_v4(y_box + row_off + ((c ^ sw) << 4));
-          __syncwarp();
-          if (lane == 0) {
-            // prefetch the next saved-activation box (next column chunk, or the first one of the next tile)
-            int nt = tile, nj = jj + 1;
-            if (nj == BN / 64) { nj = 0; nt = tile + gridDim.x; }
-            if (nt < total_tiles) {
-              const int nm0 = (nt / tiles_n) * BM, nn0 = (nt % tiles_n) * BN;
-              mbar_arrive_expect_tx(y_bar(q), Cfg::EPI_BOX_BYTES);
-              tma_load_2d(y_box, &tmap_y, y_bar(q), nn0 + nj * 64, nm0 + q * 32);
-            }
-          }
+          for (int c = 0; c < 8; ++c) yv[c] = ld_shared_v4(box + row_off + ((c ^ sw) << 4));
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -218,15 +250,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           tmem_ld_wait();
           float x[32];
           if (EPI == EPI_FWD) {
-            const uint32_t bsm = bias_smem + (acc * BN + jj * 64 + h * 32) * 4u;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint4 bb = ld_shared_v4(bsm + 16u * i);
-              x[4 * i + 0] = act_fwd(__uint_as_float(v[4 * i + 0]) + __uint_as_float(bb.x), p.act);
-              x[4 * i + 1] = act_fwd(__uint_as_float(v[4 * i + 1]) + __uint_as_float(bb.y), p.act);
-              x[4 * i + 2] = act_fwd(__uint_as_float(v[4 * i + 2]) + __uint_as_float(bb.z), p.act);
-              x[4 * i + 3] = act_fwd(__uint_as_float(v[4 * i + 3]) + __uint_as_float(bb.w), p.act);
-            }
+            const uint32_t bsm = bias_smem + (jj * 64 + h * 32) * 4u;
+            if (p.act == ACT_RELU) fwd_math<ACT_RELU>(v, bsm, x);
+            else if (p.act == ACT_SIGMOID) fwd_math<ACT_SIGMOID>(v, bsm, x);
+            else if (p.act == ACT_SIGMOID_FAST) fwd_math<ACT_SIGMOID_FAST>(v, bsm, x);
+            else fwd_math<ACT_NONE>(v, bsm, x);
             if (p.out_f32 && jj == 0 && h == 0 && n0 == 0 && row < p.M) {
               float* o = p.out_f32 + (size_t)row * p.n_valid;
               if (p.n_valid == 4) {
@@ -239,27 +267,41 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             }
           } else {
             const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yv[4 * h]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
-              x[2 * i] = __uint_as_float(v[2 * i]) * act_bwd(y_lo, p.act);
-              x[2 * i + 1] = __uint_as_float(v[2 * i + 1]) * act_bwd(y_hi, p.act);
-            }
+            if (p.act == ACT_RELU) bwd_math<ACT_RELU>(v, yw, x);
+            else if (p.act == ACT_SIGMOID) bwd_math<ACT_SIGMOID>(v, yw, x);
+            else bwd_math<ACT_NONE>(v, yw, x);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) packed[16 * h + i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
         }
-        if (tma_out) {
-          if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has finished reading out_box
+        if (EPI == EPI_DGRAD) {
+          if (lane == 0) {
+            // the store that used the other box (previous chunk) must have finished reading it; then prefetch the
+            // next saved-activation box into it (next column chunk, or the first one of the next tile)
+            tma_store_wait_read<0>();
+            int nt = tile, nj = jj + 1;
+            if (nj == BN / 64) { nj = 0; nt = tile + gridDim.x; }
+            if (nt < total_tiles) {
+              const int nm0 = (nt / tiles_n) * BM, nn0 = (nt % tiles_n) * BN;
+              mbar_arrive_expect_tx(y_bar(2 * q + (b ^ 1u)), Cfg::EPI_BOX_BYTES);
+              tma_load_2d(box0 + (b ^ 1u) * Cfg::EPI_BOX_BYTES, &tmap_y, y_bar(2 * q + (b ^ 1u)), nn0 + nj * 64,
+                          nm0 + q * 32);
+            }
+          }
           __syncwarp();
+        } else if (tma_out) {
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago (same box) has read it
+          __syncwarp();
+        }
+        if (tma_out) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            st_shared_v4(out_box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2],
+            st_shared_v4(box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2],
                          packed[4 * c + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_out, out_box, n0 + jj * 64, m0 + q * 32);
+            tma_store_2d(&tmap_out, box, n0 + jj * 64, m0 + q * 32);
             tma_store_commit();
           }
         }
@@ -572,7 +614,9 @@ int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, i
   MIP_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "linear_fwd: bad shape M=%d N=%d K=%d (K %% 64 != 0?)", M, N, K);
   MIP_REQUIRE(!out_f32 || (n_valid >= 1 && n_valid <= 8), "linear_fwd: n_valid=%d outside [1,8]", n_valid);
   MIP_REQUIRE(act >= 0 && act <= 2, "linear_fwd: act=%d", act);
-  LinearParams p{bias, out_bf16, out_f32, M, N, K, act, n_valid};
+  // trunk Sigmoid with bf16-only output: single-MUFU tanh form; fp32 head outputs keep the exact form
+  const int act_k = (act == ACT_SIGMOID && !out_f32) ? ACT_SIGMOID_FAST : act;
+  LinearParams p{bias, out_bf16, out_f32, M, N, K, act_k, n_valid};
   return dispatch_linear<EPI_FWD>(X, W, nullptr, p, (cudaStream_t)stream);
 }
 
