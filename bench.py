@@ -306,8 +306,13 @@ def main():
             json.dump(dict(ms_per_step=ms_step, kernel_ms_per_step=kernel_ms, kernels=rows), open(args.kernel_table, "w"),
                       indent=1)
         top = rows[0]
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel/shape from the committed ncu --set full capture
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f'{top["kernel"]}{tuple(top["args"][:3])}')
         roof = dict(bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"], frac=top["frac"],
-                    traffic=None, kernel=f'{top["kernel"]}{tuple(top["args"])}', share_of_step=top["share"],
+                    traffic=traffic, kernel=f'{top["kernel"]}{tuple(top["args"])}', share_of_step=top["share"],
                     peak_source=pk["src"] + " (sustained bf16)" if top["bound"] == "tensor" else pk["src"])
         total_rays = args.rays * world
         out = {

@@ -363,7 +363,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.K_in / BN;               // along input features
-  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  // split-major: the CTAs of one split (same sample range, all output tiles) are adjacent in launch order, run
+  // concurrently and share their dY / X rows through L2 instead of re-reading them from HBM
+  const int num_tiles = ((p.N_out + BM - 1) / BM) * tiles_n;
+  const int tile = blockIdx.x % num_tiles, split = blockIdx.x / num_tiles;
   const int f0 = (tile / tiles_n) * BM;          // output-feature offset (rows of dW)
   const int i0 = (tile % tiles_n) * BN;          // input-feature offset (cols of dW)
   const int kb_total = (p.M + BK - 1) / BK;

@@ -35,6 +35,17 @@ def lr_at(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.
     return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
 
 
+def sharded_loss_nerf(rgb, pixels, world, group=None):
+    """loss.py:23-40 on a ray shard: the mse inside the log is the one of the concatenated batch, so that
+    SUM-all-reduced gradients equal the unsharded gradients.  Pure torch + one scalar all-reduce."""
+    sq = ((rgb[..., :3] - pixels[..., :3]) ** 2).sum()
+    tot = sq.detach().clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    mse = (sq + (tot - sq.detach())) / (rgb.shape[0] * world)
+    psnr = mse_to_psnr(mse)
+    return -psnr + 30, psnr
+
+
 class FlatAdamW:
     """torch.optim.AdamW semantics (train.py:38) over per-net flat buffers.  Like torch >= 2.0, parameters
     without a gradient are skipped: `step(names)` updates only the nets that were just back-propagated."""
@@ -109,15 +120,9 @@ class Trainer:
         return ops.interlevel_loss(w_hat, bound_total=total, batch_div=batch)
 
     def _loss_nerf(self, rgb, pixels):
-        """loss.py:23-40; sharded: the mse inside the log is the one of the concatenated batch."""
         if self.world == 1:
             return Loss_nerf(rgb, pixels)
-        sq = ((rgb[..., :3] - pixels[..., :3]) ** 2).sum()
-        tot = sq.detach().clone()
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        mse = (sq + (tot - sq.detach())) / (rgb.shape[0] * self.world)
-        psnr = mse_to_psnr(mse)
-        return -psnr + 30, psnr
+        return sharded_loss_nerf(rgb, pixels, self.world)
 
     # -- one reference iteration -------------------------------------------------------------------
     def step(self, rays, pixels):

@@ -556,3 +556,18 @@ def test_inputs_not_mutated_and_render_image():
 def test_cpu_tensors_are_rejected(ops):
     with pytest.raises(RuntimeError):
         ops.viewdir_enc(torch.randn(4, 3))
+
+
+def test_render_image_distributed_single_rank():
+    """world_size 1: the ray-partitioned renderer equals the model's own chunk loop on the same chunk boundaries."""
+    from mipnerf360_b200.model import mipNeRF360
+    from mipnerf360_b200.render import render_image_distributed
+    torch.manual_seed(3)
+    m = mipNeRF360(randomized=False, num_samples=64, hidden_proposal=64, hidden_nerf=128, device=torch.device(DEV))
+    rays_c, rays = make_rays(6 * 10, 9)
+    rgb, dist, acc = render_image_distributed(m, rays_c, 6, 10, chunks=32)
+    img, dist2, acc2 = m.render_image(rays_c, 6, 10, chunks=32)
+    assert rgb.shape == (6, 10, 3)
+    close(dist, torch.from_numpy(dist2), atol=0)
+    close(acc, torch.from_numpy(acc2), atol=0)
+    assert (torch.from_numpy(img).float() - (rgb.clamp(0, 1) * 255).cpu().floor()).abs().max() <= 1
