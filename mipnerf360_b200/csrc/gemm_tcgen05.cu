@@ -25,20 +25,26 @@ constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, war
 enum { EPI_FWD = 0, EPI_DGRAD = 1 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_SIGMOID_FAST = 3 /* internal: bf16-only outputs */ };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
+// each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB (6 stages
+// instead of 4 in the same shared memory) and B is fetched from L2 once per pair.
+template <int BN, int CG = 1>
 struct LinearCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256) ? (CG == 1 ? 4 : 5) : (BN >= 128 ? 5 : 6);
+  // epilogue boxes per warp: 3 when shared memory allows (the saved-activation box of dgrad is then
+  // prefetched a whole chunk ahead), else 2
+  static constexpr int NBOX = (BN >= 256 && CG == 1) ? 2 : 3;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two >= 32)
   // epilogue staging: per epilogue warp one 4 KB [32 rows x 64 cols] bf16 box for the TMA store, and a second
   // region of the same size that holds the saved-activation box (dgrad) or, shared by all warps, the bias
   // tile of the two accumulator stages (fwd)
   static constexpr int EPI_BOX_BYTES = 32 * 64 * 2;
-  static constexpr int EPI_BYTES = 2 * 4 * EPI_BOX_BYTES + 1024 /* bias tile: up to 256 floats */;
+  static constexpr int EPI_BYTES = NBOX * 4 * EPI_BOX_BYTES + 1024 /* bias tile: up to 256 floats */;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 struct LinearParams {
@@ -105,12 +111,12 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_y,
               const LinearParams p) {
-  using Cfg = LinearCfg<BN>;
+  using Cfg = LinearCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
@@ -119,11 +125,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
-  auto y_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + i); };   // 2*6+4+8 = 24 barriers max
-  const uint32_t tmem_slot = bar_base + 8u * 24;
+  auto y_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + i); };   // 2*6+4+12 = 28 barriers max
+  const uint32_t tmem_slot = bar_base + 8u * 28;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = p.N / BN;
+  // scheduling unit = CTA (CG 1) or CTA pair (CG 2); `rank` = position inside the pair
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, nunits = gridDim.x / CG;
+  const int tiles_m = (p.M + BM * CG - 1) / (BM * CG), tiles_n = p.N / BN;
   const int total_tiles = tiles_m * tiles_n;
   const int kblocks = p.K / BK;
 
@@ -134,9 +143,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 4 * CG);  // CG 2: the leader's barrier collects both CTAs' epilogue warps
     }
-    for (int i = 0; i < 8; ++i) mbar_init(y_bar(i), 1);
+    for (int i = 0; i < 4 * Cfg::NBOX; ++i) mbar_init(y_bar(i), 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -144,37 +153,43 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if (EPI == EPI_DGRAD) prefetch_tmap(&tmap_y);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish<CG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();  // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer (one per CTA; CG 2: both CTAs signal the LEADER's full barrier) =====
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
+        const int m0 = (tile / tiles_n) * (BM * CG) + rank * BM, n0 = (tile % tiles_n) * BN + rank * (BN / CG) * (CG - 1);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * BK, n0);
+          if (CG == 1) {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * BK, n0);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+            tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (CG 2: the leader CTA issues M = 256 MMAs for the pair) =====
+      constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0, BM * CG);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += nunits) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -187,12 +202,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs have read it
+          umma_commit<CG>(empty_bar(stage));  // frees the smem slot (in both CTAs) when these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete
+        umma_commit<CG>(tfull_bar(acc));  // accumulator complete (signalled to both CTAs' epilogues)
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -204,20 +219,26 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     // dgrad: the box first receives the saved-activation tile by TMA (prefetched one chunk ahead), each lane
     // reads its own row, and the result is written back in place before the box is stored.
     const int q = warp & 3;
-    const uint32_t box0 = epi_base + q * 2 * Cfg::EPI_BOX_BYTES;
-    const uint32_t bias_smem = epi_base + 8 * Cfg::EPI_BOX_BYTES;  // fwd: BN floats, shared by the 4 warps
+    constexpr int NBOX = Cfg::NBOX;
+    const uint32_t box0 = epi_base + q * NBOX * Cfg::EPI_BOX_BYTES;
+    const uint32_t bias_smem = epi_base + 4 * NBOX * Cfg::EPI_BOX_BYTES;  // fwd: BN floats, shared by the 4 warps
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const bool tma_out = p.out_bf16 != nullptr;
-    uint32_t acc = 0, acc_phase = 0, cnt = 0;
+    uint32_t acc = 0, acc_phase = 0;
+    uint32_t bi = 0, bphase = 0;  // current box of this warp and the parity of its saved-activation barrier
     int bias_n0 = -1;
-    if (EPI == EPI_DGRAD && lane == 0 && (int)blockIdx.x < total_tiles) {
-      const int m0 = (blockIdx.x / tiles_n) * BM, n0 = (blockIdx.x % tiles_n) * BN;
-      mbar_arrive_expect_tx(y_bar(2 * q), Cfg::EPI_BOX_BYTES);
-      tma_load_2d(box0, &tmap_y, y_bar(2 * q), n0, m0 + q * 32);
-    }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    // issue the TMA load of the saved-activation box for column chunk (nt, nj) into box `nb`
+    auto load_y = [&](int nt, int nj, uint32_t nb) {
+      if (nt < total_tiles) {
+        const int nm0 = (nt / tiles_n) * (BM * CG) + rank * BM, nn0 = (nt % tiles_n) * BN;
+        mbar_arrive_expect_tx(y_bar(NBOX * q + nb), Cfg::EPI_BOX_BYTES);
+        tma_load_2d(box0 + nb * Cfg::EPI_BOX_BYTES, &tmap_y, y_bar(NBOX * q + nb), nn0 + nj * 64, nm0 + q * 32);
+      }
+    };
+    if (EPI == EPI_DGRAD && lane == 0) load_y(unit, 0, 0);
+    for (int tile = unit; tile < total_tiles; tile += nunits) {
+      const int m0 = (tile / tiles_n) * (BM * CG) + rank * BM, n0 = (tile % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
       if (EPI == EPI_FWD && n0 != bias_n0) {
         // bias tile into shared memory (read back as broadcasts).  With gridDim.x a multiple of the number
@@ -233,13 +254,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int jj = 0; jj < BN / 64; ++jj, ++cnt) {
-        const uint32_t b = cnt & 1u;
-        const uint32_t box = box0 + b * Cfg::EPI_BOX_BYTES;
+      for (int jj = 0; jj < BN / 64; ++jj) {
+        const uint32_t box = box0 + bi * Cfg::EPI_BOX_BYTES;
+        const uint32_t nbi = (bi + 1 == NBOX) ? 0u : bi + 1;
+        int nt = tile, nj = jj + 1;  // the chunk after this one
+        if (nj == BN / 64) { nj = 0; nt = tile + nunits; }
         uint32_t packed[32];  // 64 bf16 of this lane's row
         uint4 yv[8];
         if (EPI == EPI_DGRAD) {
-          mbar_wait(y_bar(2 * q + b), (cnt >> 1) & 1u);
+          if (NBOX >= 3 && lane == 0) {
+            // three boxes: the next box was last read by the store issued two chunks ago -> prefetch now, a
+            // whole chunk ahead of its use
+            tma_store_wait_read<1>();
+            load_y(nt, nj, nbi);
+          }
+          mbar_wait(y_bar(NBOX * q + bi), bphase);
 #pragma unroll
           for (int c = 0; c < 8; ++c) yv[c] = ld_shared_v4(box + row_off + ((c ^ sw) << 4));
         }
@@ -275,22 +304,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           for (int i = 0; i < 16; ++i) packed[16 * h + i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
         }
         if (EPI == EPI_DGRAD) {
-          if (lane == 0) {
-            // the store that used the other box (previous chunk) must have finished reading it; then prefetch the
-            // next saved-activation box into it (next column chunk, or the first one of the next tile)
+          if (NBOX == 2 && lane == 0) {
+            // two boxes: the store that used the other box (previous chunk) must have finished reading it before
+            // the next saved-activation box can be fetched into it
             tma_store_wait_read<0>();
-            int nt = tile, nj = jj + 1;
-            if (nj == BN / 64) { nj = 0; nt = tile + gridDim.x; }
-            if (nt < total_tiles) {
-              const int nm0 = (nt / tiles_n) * BM, nn0 = (nt % tiles_n) * BN;
-              mbar_arrive_expect_tx(y_bar(2 * q + (b ^ 1u)), Cfg::EPI_BOX_BYTES);
-              tma_load_2d(box0 + (b ^ 1u) * Cfg::EPI_BOX_BYTES, &tmap_y, y_bar(2 * q + (b ^ 1u)), nn0 + nj * 64,
-                          nm0 + q * 32);
-            }
+            load_y(nt, nj, nbi);
           }
           __syncwarp();
         } else if (tma_out) {
-          if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago (same box) has read it
+          if (lane == 0) tma_store_wait_read<NBOX - 1>();  // the store that last used this box has read it
           __syncwarp();
         }
         if (tma_out) {
@@ -305,20 +327,25 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             tma_store_commit();
           }
         }
+        bi = nbi;
+        if (bi == 0) bphase ^= 1u;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);  // the MMA issuer lives in the leader CTA
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();  // the peer may still signal barriers in this CTA's smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -546,26 +573,43 @@ static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long lon
   return MIP360_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
                          cudaStream_t stream) {
-  using Cfg = LinearCfg<BN>;
+  using Cfg = LinearCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   CUtensorMap ta, tb, tout, ty;
   int rc;
   if ((rc = make_tmap(&ta, A, p.M, p.K, BM)) != MIP360_OK) return rc;
-  if ((rc = make_tmap(&tb, Bw, p.N, p.K, BN)) != MIP360_OK) return rc;
+  if ((rc = make_tmap(&tb, Bw, p.N, p.K, BN / CG)) != MIP360_OK) return rc;
   tout = ta;
   ty = ta;
   if (p.out_bf16 && (rc = make_tmap(&tout, p.out_bf16, p.M, p.N, 32)) != MIP360_OK) return rc;
   if (EPI == EPI_DGRAD && (rc = make_tmap(&ty, yprev, p.M, p.N, 32)) != MIP360_OK) return rc;
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
+  const int tiles = ((p.M + BM * CG - 1) / (BM * CG)) * (p.N / BN);
+  const int units = sm_count() / CG;
+  const int grid = (tiles < units ? tiles : units) * CG;
+  if (CG == 1) {
+    linear_kernel<BN, EPI, CG><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MIP_CUDA(cudaLaunchKernelEx(&cfg, linear_kernel<BN, EPI, CG>, ta, tb, tout, ty, p));
+  }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -573,9 +617,13 @@ static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* 
 template <int EPI>
 static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
                            cudaStream_t stream) {
-  if (p.N % 256 == 0) return launch_linear<256, EPI>(A, Bw, yprev, p, stream);
-  if (p.N == 128) return launch_linear<128, EPI>(A, Bw, yprev, p, stream);
-  if (p.N == 64) return launch_linear<64, EPI>(A, Bw, yprev, p, stream);
+  // CTA pairs (cta_group::2) for the big layers; single CTAs when there are too few 256-row tiles to fill the pairs
+  static const bool pair_ok = getenv("MIP360_NO_CTA_PAIR") == nullptr;
+  if (p.N % 256 == 0 && p.K >= 512 && pair_ok && p.M >= 256 * (sm_count() / 2))
+    return launch_linear<256, EPI, 2>(A, Bw, yprev, p, stream);
+  if (p.N % 256 == 0) return launch_linear<256, EPI, 1>(A, Bw, yprev, p, stream);
+  if (p.N == 128) return launch_linear<128, EPI, 1>(A, Bw, yprev, p, stream);
+  if (p.N == 64) return launch_linear<64, EPI, 1>(A, Bw, yprev, p, stream);
   set_error("linear: N=%d not supported (need 64, 128 or a multiple of 256)", p.N);
   return MIP360_ERR_UNSUPPORTED;
 }
