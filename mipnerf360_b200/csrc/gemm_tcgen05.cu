@@ -356,13 +356,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 // swizzle): descriptor SBO = 1024 B between 8-row groups along the reduction, LBO = 8192 B between
 // 64-feature chunks; one K=16 MMA consumes two 8-row groups (2048 B).
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+// CG = 2: CTA pair, M = 256 output features (128 per CTA), each CTA stages half of the BN input features.
+template <int BN, int CG = 1>
 struct WgradCfg {
   static constexpr int BOX_BYTES = 64 * 64 * 2;  // 8 KB
-  static constexpr int A_BYTES = 2 * BOX_BYTES;  // 128 output features
-  static constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+  static constexpr int A_BYTES = 2 * BOX_BYTES;  // 128 output features per CTA
+  static constexpr int B_BOXES = BN / CG / 64;
+  static constexpr int B_BYTES = B_BOXES * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256 && CG == 1) ? 4 : 6;
   static constexpr int ONES_BYTES = 2048;
   static constexpr int TMEM_COLS = (BN >= 256) ? 512 : (BN >= 128 ? 256 : 128);  // BN accumulator columns + 16 (bias gradient)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + 1024 + 256;
@@ -374,11 +376,11 @@ struct WgradParams {
   int M, N_out, K_in, splits;
 };
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
              const WgradParams p) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ones_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -392,10 +394,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
   const int tiles_n = p.K_in / BN;               // along input features
   // split-major: the CTAs of one split (same sample range, all output tiles) are adjacent in launch order, run
   // concurrently and share their dY / X rows through L2 instead of re-reading them from HBM
-  const int num_tiles = ((p.N_out + BM - 1) / BM) * tiles_n;
-  const int tile = blockIdx.x % num_tiles, split = blockIdx.x / num_tiles;
-  const int f0 = (tile / tiles_n) * BM;          // output-feature offset (rows of dW)
-  const int i0 = (tile % tiles_n) * BN;          // input-feature offset (cols of dW)
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG;
+  const int num_tiles = ((p.N_out + BM * CG - 1) / (BM * CG)) * tiles_n;
+  const int tile = unit % num_tiles, split = unit / num_tiles;
+  const int f0 = (tile / tiles_n) * (BM * CG) + rank * BM;  // output-feature offset of THIS CTA (rows of dW)
+  const int i0 = (tile % tiles_n) * BN;                      // input-feature offset (cols of dW)
   const int kb_total = (p.M + BK - 1) / BK;
   const int kb_begin = (int)((long long)kb_total * split / p.splits);
   const int kb_end = (int)((long long)kb_total * (split + 1) / p.splits);
@@ -417,11 +421,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
   fence_proxy_async_smem();
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish<CG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -430,23 +434,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
     if (warp == 0) {
       if (lane == 0) {
         uint32_t stage = 0, phase = 0;
+        const int ib = i0 + rank * (BN / CG) * (CG - 1);  // this CTA's share of the input features
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          if (CG == 1) {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d(sa + c * Cfg::BOX_BYTES, &tmap_dy, full_bar(stage), f0 + c * 64, kb * BK);
+            for (int c = 0; c < 2; ++c)
+              tma_load_2d(sa + c * Cfg::BOX_BYTES, &tmap_dy, full_bar(stage), f0 + c * 64, kb * BK);
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(sa + Cfg::A_BYTES + c * Cfg::BOX_BYTES, &tmap_x, full_bar(stage), i0 + c * 64, kb * BK);
+            for (int c = 0; c < Cfg::B_BOXES; ++c)
+              tma_load_2d(sa + Cfg::A_BYTES + c * Cfg::BOX_BYTES, &tmap_x, full_bar(stage), ib + c * 64, kb * BK);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              tma_load_2d_pair(sa + c * Cfg::BOX_BYTES, &tmap_dy, full_bar(stage), f0 + c * 64, kb * BK);
+#pragma unroll
+            for (int c = 0; c < Cfg::B_BOXES; ++c)
+              tma_load_2d_pair(sa + Cfg::A_BYTES + c * Cfg::BOX_BYTES, &tmap_x, full_bar(stage), ib + c * 64, kb * BK);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1);
-        constexpr uint32_t idesc_ones = make_idesc_bf16(16, 1, 1);
+      if (lane == 0 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1, BM * CG);
+        constexpr uint32_t idesc_ones = make_idesc_bf16(16, 1, 1, BM * CG);
         const uint64_t ones_desc = make_smem_desc_sw128(ones_base, Cfg::BOX_BYTES, 1024);
         uint32_t stage = 0, phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -459,13 +474,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // 16 reduction rows = 2 x 1024 B groups: +128 in the (addr >> 4) field
             const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-            umma_bf16(tmem_base, adesc + 128u * k, bdesc + 128u * k, idesc, accum);
-            if (do_bias) umma_bf16(tmem_base + BN, adesc + 128u * k, ones_desc, idesc_ones, accum);
+            umma_bf16<CG>(tmem_base, adesc + 128u * k, bdesc + 128u * k, idesc, accum);
+            if (do_bias) umma_bf16<CG>(tmem_base + BN, adesc + 128u * k, ones_desc, idesc_ones, accum);
           }
-          umma_commit(empty_bar(stage));
+          umma_commit<CG>(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar);
+        umma_commit<CG>(tfull_bar);
       }
     } else {
       const int q = warp & 3;
@@ -496,10 +511,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -628,26 +643,42 @@ static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t
   return MIP360_ERR_UNSUPPORTED;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_wgrad(const uint16_t* dY, const uint16_t* X, WgradParams p, cudaStream_t stream) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MIP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MIP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   CUtensorMap tdy, tx;
   int rc;
   if ((rc = make_tmap(&tdy, dY, p.M, p.N_out, 64)) != MIP360_OK) return rc;
   if ((rc = make_tmap(&tx, X, p.M, p.K_in, 64)) != MIP360_OK) return rc;
-  const int tiles = ((p.N_out + BM - 1) / BM) * (p.K_in / BN);
+  const int tiles = ((p.N_out + BM * CG - 1) / (BM * CG)) * (p.K_in / BN);
   const int kb_total = (p.M + BK - 1) / BK;
-  // two waves of CTAs when there is enough reduction depth, at least 8 k-blocks per split
-  int splits = (2 * sm_count()) / tiles;
+  // two waves of CTAs (CTA pairs) when there is enough reduction depth, at least 8 k-blocks per split
+  int splits = (2 * (sm_count() / CG)) / tiles;
   if (splits < 1) splits = 1;
   if (splits > kb_total / 8) splits = kb_total / 8 > 0 ? kb_total / 8 : 1;
   p.splits = splits;
-  wgrad_kernel<BN><<<tiles * splits, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tdy, tx, p);
+  if (CG == 1) {
+    wgrad_kernel<BN, CG><<<tiles * splits, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tdy, tx, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles * splits * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MIP_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel<BN, CG>, tdy, tx, p));
+  }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -686,9 +717,11 @@ int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int
   MIP_REQUIRE(dY && X && dW, "linear_wgrad: null pointer");
   MIP_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0 && K % 64 == 0, "linear_wgrad: bad shape M=%d N=%d K=%d", M, N, K);
   WgradParams p{dW, db, M, N, K, 1};
-  if (K % 256 == 0) return launch_wgrad<256>(dY, X, p, (cudaStream_t)stream);
-  if (K == 128) return launch_wgrad<128>(dY, X, p, (cudaStream_t)stream);
-  if (K == 64) return launch_wgrad<64>(dY, X, p, (cudaStream_t)stream);
+  static const bool pair_ok = getenv("MIP360_NO_CTA_PAIR") == nullptr;
+  if (K % 256 == 0 && N % 256 == 0 && N >= 512 && pair_ok) return launch_wgrad<256, 2>(dY, X, p, (cudaStream_t)stream);
+  if (K % 256 == 0) return launch_wgrad<256, 1>(dY, X, p, (cudaStream_t)stream);
+  if (K == 128) return launch_wgrad<128, 1>(dY, X, p, (cudaStream_t)stream);
+  if (K == 64) return launch_wgrad<64, 1>(dY, X, p, (cudaStream_t)stream);
   set_error("linear_wgrad: K=%d not supported (need 64, 128 or a multiple of 256)", K);
   return MIP360_ERR_UNSUPPORTED;
 }
