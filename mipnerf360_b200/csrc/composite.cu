@@ -3,6 +3,7 @@
 // and per-sample values are staged in shared memory with coalesced loads, each lane owns a contiguous
 // chunk of ceil(N/32) intervals, the transmittance is a warp exclusive scan.
 #include "common.cuh"
+#include "ray_group.cuh"
 
 namespace mip360 {
 
@@ -207,6 +208,208 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N in {32, 64, 128}: 8 lanes per ray, E = N/8 intervals per lane in registers (ray_group.cuh)
+// ---------------------------------------------------------------------------------------------------
+template <int E>
+struct RgRay {
+  float t[E + 1], sigma[E], aux[E], delta[E], dd[E], T[E], w[E];
+};
+
+// loads knots + densities (+ activation), forms the weights of the lane's E intervals
+template <int E>
+__device__ __forceinline__ void rg_weights(RgRay<E>& r, const float* __restrict__ rgb_or_raw,
+                                           const float* __restrict__ density, const float* __restrict__ t_vals,
+                                           const float* __restrict__ dirs, long long ray, int N, int gl, int head_mode,
+                                           int density_mode, float density_bias) {
+  const int j0 = gl * E;
+  rg_load_knots<E>(t_vals + ray * (N + 1), j0, r.t);
+  if (head_mode == 1) {
+    const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + ray * N + j0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      r.aux[i] = __ldg(raw4 + i).x;
+      r.sigma[i] = softplus_f(r.aux[i] + density_bias);
+    }
+  } else {
+    rg_load<E>(density + ray * N + j0, r.aux);
+#pragma unroll
+    for (int i = 0; i < E; ++i) r.sigma[i] = density_mode == 1 ? softplus_f(r.aux[i] + density_bias) : r.aux[i];
+  }
+  const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float run = 0.f, excl[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    r.delta[i] = (r.t[i + 1] - r.t[i]) * dnorm;
+    r.dd[i] = r.sigma[i] * r.delta[i];
+    excl[i] = run;
+    run += r.dd[i];
+  }
+  const float off = rg_scan_excl(run, gl);
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    r.T[i] = expf(-(off + excl[i]));
+    r.w[i] = (1.f - expf(-r.dd[i])) * r.T[i];
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void rg_load_rgb(float (&c)[E][3], const float* __restrict__ rgb_or_raw, long long ray, int N,
+                                            int j0, int head_mode, float rgb_padding) {
+  if (head_mode == 1) {
+    const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + ray * N + j0;
+    const float scale = 1.f + 2.f * rgb_padding;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float4 v = __ldg(raw4 + i);
+      c[i][0] = v.y * scale - rgb_padding;
+      c[i][1] = v.z * scale - rgb_padding;
+      c[i][2] = v.w * scale - rgb_padding;
+    }
+  } else {
+    float flat[3 * E];
+    rg_load<3 * E>(rgb_or_raw + (ray * N + j0) * 3, flat);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      c[i][0] = flat[3 * i]; c[i][1] = flat[3 * i + 1]; c[i][2] = flat[3 * i + 2];
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
+                        const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
+                        int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                        float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
+                        float* __restrict__ weights) {
+  constexpr int N = E * RG_LANES;
+  const int gl = threadIdx.x & 7, j0 = gl * E;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + (threadIdx.x >> 3);
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    RgRay<E> r;
+    rg_weights<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, density_mode, density_bias);
+    if (weights && active) rg_store<E>(weights + ray * N + j0, r.w);
+    if (weights_only) continue;
+    float c[E][3];
+    rg_load_rgb<E>(c, rgb_or_raw, ray, N, j0, head_mode, rgb_padding);
+    float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      a += r.w[i];
+      cr += r.w[i] * c[i][0];
+      cg += r.w[i] * c[i][1];
+      cb += r.w[i] * c[i][2];
+      wt += r.w[i] * (0.5f * (r.t[i] + r.t[i + 1]));
+    }
+    a = rg_sum(a); cr = rg_sum(cr); cg = rg_sum(cg); cb = rg_sum(cb); wt = rg_sum(wt);
+    const float t_first = __shfl_sync(FULL_MASK, r.t[0], 0, RG_LANES);
+    const float t_last = __shfl_sync(FULL_MASK, r.t[E], RG_LANES - 1, RG_LANES);
+    if (gl == 0 && active) {
+      float dist = nan_to_num_f(wt / a);
+      dist = fminf(fmaxf(dist, t_first), t_last);
+      if (white_bkgd) {
+        const float bg = 1.f - a;
+        cr += bg; cg += bg; cb += bg;
+      }
+      comp_rgb[ray * 3 + 0] = cr;
+      comp_rgb[ray * 3 + 1] = cg;
+      comp_rgb[ray * 3 + 2] = cb;
+      distance[ray] = dist;
+      acc_out[ray] = a;
+    }
+  }
+}
+
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
+                        const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
+                        int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                        const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
+                        float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw) {
+  constexpr int N = E * RG_LANES;
+  const int gl = threadIdx.x & 7, j0 = gl * E;
+  const float cscale = 1.f + 2.f * rgb_padding;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + (threadIdx.x >> 3);
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    RgRay<E> r;
+    rg_weights<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, density_mode, density_bias);
+    float c[E][3];
+    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+    if (!weights_only) {
+      rg_load_rgb<E>(c, rgb_or_raw, ray, N, j0, head_mode, rgb_padding);
+      if (g_rgb) { gr = __ldg(g_rgb + ray * 3); gg = __ldg(g_rgb + ray * 3 + 1); gb = __ldg(g_rgb + ray * 3 + 2); }
+      if (g_acc) ga = __ldg(g_acc + ray);
+      if (white_bkgd) ga -= (gr + gg + gb);
+    }
+    float G[E];
+    if (g_w) {
+      rg_load<E>(g_w + ray * N + j0, G);
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; ++i) G[i] = 0.f;
+    }
+    float run = 0.f, excl_rev[E];
+#pragma unroll
+    for (int i = E - 1; i >= 0; --i) {
+      G[i] += ga;
+      if (!weights_only) G[i] += gr * c[i][0] + gg * c[i][1] + gb * c[i][2];
+      excl_rev[i] = run;
+      run += G[i] * r.w[i];
+    }
+    const float off = rg_scan_excl_rev(run, gl);
+    float gs[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float g_dd = G[i] * r.T[i] * expf(-r.dd[i]) - (off + excl_rev[i]);
+      gs[i] = g_dd * r.delta[i];
+    }
+    if (!active) continue;
+    if (head_mode == 1) {
+      float4* out = reinterpret_cast<float4*>(g_raw) + ray * N + j0;
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        out[i] = make_float4(gs[i] * sigmoid_f(r.aux[i] + density_bias), r.w[i] * gr * cscale, r.w[i] * gg * cscale,
+                             r.w[i] * gb * cscale);
+    } else {
+      if (g_density) {
+        if (density_mode == 1) {
+#pragma unroll
+          for (int i = 0; i < E; ++i) gs[i] *= sigmoid_f(r.aux[i] + density_bias);
+        }
+        rg_store<E>(g_density + ray * N + j0, gs);
+      }
+      if (!weights_only && g_rgb_in) {
+        float flat[3 * E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+          flat[3 * i] = r.w[i] * gr; flat[3 * i + 1] = r.w[i] * gg; flat[3 * i + 2] = r.w[i] * gb;
+        }
+        rg_store<3 * E>(g_rgb_in + (ray * N + j0) * 3, flat);
+      }
+    }
+  }
+}
+
+template <typename... Args>
+static void launch_composite_fwd(int N, int B, cudaStream_t st, Args... a) {
+  if (N == 32) composite_fwd_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else if (N == 64) composite_fwd_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else composite_fwd_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+}
+template <typename... Args>
+static void launch_composite_bwd(int N, int B, cudaStream_t st, Args... a) {
+  if (N == 32) composite_bwd_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else if (N == 64) composite_bwd_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else composite_bwd_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+}
+
 // intern/parameterization.py:5-8 with the eps shifts a single reference call observes (App. A4)
 __global__ void __launch_bounds__(256)
 t_to_s_kernel(const float* __restrict__ t_vals, const float* __restrict__ near, const float* __restrict__ far, int B,
@@ -282,9 +485,13 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
   MIP_REQUIRE(head_mode == 1 || density, "composite_fwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
-      distance, acc, weights);
+  if (rg_supported_host(N))
+    launch_composite_fwd(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
+                         rgb_padding, white_bkgd, comp_rgb, distance, acc, weights);
+  else
+    composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
+        distance, acc, weights);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -297,9 +504,13 @@ int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const fl
   MIP_REQUIRE(head_mode == 1 || density, "composite_bwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
-      g_w, g_rgb_in, g_density, g_raw);
+  if (rg_supported_host(N))
+    launch_composite_bwd(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
+                         rgb_padding, white_bkgd, g_rgb, g_acc, g_w, g_rgb_in, g_density, g_raw);
+  else
+    composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
+        g_w, g_rgb_in, g_density, g_raw);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -309,9 +520,13 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
   MIP_REQUIRE(density && t_vals && dirs && weights, "density_to_weight_fwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
-      weights);
+  if (rg_supported_host(N))
+    launch_composite_fwd(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
+                         density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights);
+  else
+    composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
+        weights);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -322,9 +537,14 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
   MIP_REQUIRE(density && t_vals && dirs && g_w && g_density, "density_to_weight_bwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, g_w, nullptr,
-      g_density, nullptr);
+  if (rg_supported_host(N))
+    launch_composite_bwd(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
+                         density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, g_w, (float*)nullptr,
+                         g_density, (float*)nullptr);
+  else
+    composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, g_w, nullptr,
+        g_density, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -116,6 +116,43 @@ __device__ __forceinline__ void ipe_features(const float mean[3], const float co
   }
 }
 
+// Fast variant for the bf16 MLP rows (model path): the 21 directions are compile-time immediates (zero terms
+// vanish), sigma uses the symmetric 6-term form with FMAs, exp/sin/cos are the MUFU approximations after an
+// explicit range reduction (abs. error ~5e-7, far below the bf16 rounding of the result: 2^-9 relative).
+// Output: 21 packed bf16 pairs = columns 0..41 of the MLP row.
+__device__ __forceinline__ void ipe_features_bf16(const float mean[3], const float cov[9], uint32_t packed[21]) {
+  constexpr float A = 0.8506508f, B = 0.5257311f, C = 0.809017f, D = 0.5f, E = 0.309017f;
+  constexpr float P[21][3] = {{A, 0, B},  {C, D, E},  {B, A, 0},  {1, 0, 0},   {C, D, -E},  {A, 0, -B}, {E, C, -D},
+                              {0, B, -A}, {D, E, -C}, {0, 1, 0},  {-B, A, 0},  {-E, C, -D}, {0, B, A},  {-E, C, D},
+                              {E, C, D},  {D, E, C},  {D, -E, C}, {0, 0, 1},   {-D, E, C},  {-C, D, E}, {-C, D, -E}};
+  float sn[21], cs[21];
+  const float c01 = cov[1] + cov[3], c02 = cov[2] + cov[6], c12 = cov[5] + cov[7];  // symmetric part x 2
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    const float p0 = P[k][0], p1 = P[k][1], p2 = P[k][2];
+    float gamma = 0.f, sigma = 0.f;
+    if (p0 != 0.f) gamma = fmaf(p0, mean[0], gamma);
+    if (p1 != 0.f) gamma = fmaf(p1, mean[1], gamma);
+    if (p2 != 0.f) gamma = fmaf(p2, mean[2], gamma);
+    if (p0 != 0.f) sigma = fmaf(p0 * p0, cov[0], sigma);
+    if (p1 != 0.f) sigma = fmaf(p1 * p1, cov[4], sigma);
+    if (p2 != 0.f) sigma = fmaf(p2 * p2, cov[8], sigma);
+    if (p0 * p1 != 0.f) sigma = fmaf(p0 * p1, c01, sigma);
+    if (p0 * p2 != 0.f) sigma = fmaf(p0 * p2, c02, sigma);
+    if (p1 * p2 != 0.f) sigma = fmaf(p1 * p2, c12, sigma);
+    const float damp = exp2f(-0.72134752f * sigma);  // exp(-sigma/2) = 2^(-sigma/(2 ln 2)): one MUFU.EX2
+    const float kf = rintf(gamma * 0.15915494f);      // range reduction to [-pi, pi]
+    const float r = fmaf(kf, -6.2831855f, gamma);
+    sn[k] = damp * __sinf(r);
+    cs[k] = damp * __cosf(r);
+  }
+#pragma unroll
+  for (int c = 0; c < 10; ++c) packed[c] = pack_bf16x2(sn[2 * c], sn[2 * c + 1]);
+  packed[10] = pack_bf16x2(sn[20], cs[0]);
+#pragma unroll
+  for (int c = 0; c < 10; ++c) packed[11 + c] = pack_bf16x2(cs[2 * c + 1], cs[2 * c + 2]);
+}
+
 constexpr int K1_THREADS = 256;
 constexpr int K1_STAGE_FLOATS = 32 * 43;  // per-warp staging: 32 rows x (42 + 1 pad) floats
 
@@ -135,6 +172,7 @@ __device__ __forceinline__ void warp_store_rows(float* stage, const float* vals,
   __syncwarp();
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(K1_THREADS)
 cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
                 const float* __restrict__ origins, const float* __restrict__ directions,
@@ -171,29 +209,36 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
     for (int i = 0; i < 3; ++i) mean[i] = mean[i] + origins[b * 3 + i];
   }
 
-  if (means_out) warp_store_rows<3>(stage, mean, means_out + warp_s0 * 3, lane, rows_valid);
-  if (covs_out) warp_store_rows<9>(stage, cov, covs_out + warp_s0 * 9, lane, rows_valid);
-  if (!enc_out && !x_out) return;
+  uint32_t packed[32];
+  if (FAST) {
+    // model path: only the bf16 MLP rows are wanted
+    ipe_features_bf16(mean, cov, packed);
+  } else {
+    if (means_out) warp_store_rows<3>(stage, mean, means_out + warp_s0 * 3, lane, rows_valid);
+    if (covs_out) warp_store_rows<9>(stage, cov, covs_out + warp_s0 * 9, lane, rows_valid);
+    if (!enc_out && !x_out) return;
 
-  // features into the staging tile: row = lane, leading dimension 43
-  float* row = stage + lane * 43;
-  ipe_features(mean, cov, true, row, row + 21, 1);
-  __syncwarp();
-  if (enc_out) {
-    float* g = enc_out + warp_s0 * 42;
-    const int total = rows_valid * 42;
-    for (int e = lane; e < total; e += 32) {
-      const int r = e / 42, c = e - r * 42;
-      g[e] = stage[r * 43 + c];
+    // features into the staging tile: row = lane, leading dimension 43
+    float* row = stage + lane * 43;
+    ipe_features(mean, cov, true, row, row + 21, 1);
+    __syncwarp();
+    if (enc_out) {
+      float* g = enc_out + warp_s0 * 42;
+      const int total = rows_valid * 42;
+      for (int e = lane; e < total; e += 32) {
+        const int r = e / 42, c = e - r * 42;
+        g[e] = stage[r * 43 + c];
+      }
+    }
+    if (x_out) {
+#pragma unroll
+      for (int c = 0; c < 21; ++c) packed[c] = pack_bf16x2(row[2 * c], row[2 * c + 1]);
     }
   }
   if (x_out) {
     // bf16 rows of 64: [0,42) IPE, [42,58) view-direction encoding of the ray, [58,64) zeros.
     // Each lane converts its own row to 8 x 16-byte chunks, stored XOR-swizzled, then the warp writes
     // its 4 KB (32 rows x 128 B, contiguous in global memory) with 16-byte coalesced stores.
-    uint32_t packed[32];
-#pragma unroll
-    for (int c = 0; c < 21; ++c) packed[c] = pack_bf16x2(row[2 * c], row[2 * c + 1]);
     const float4* vd4 = reinterpret_cast<const float4*>(vdir_enc + (long long)b * 16);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -423,9 +468,14 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
   MIP_REQUIRE(!x_bf16 || vdir_enc, "cast_ipe: x_bf16 output needs vdir_enc [B,16]");
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
-  cast_ipe_kernel<<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
-      t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
-      enc, x_bf16);
+  if (x_bf16 && !means && !covs && !enc)
+    cast_ipe_kernel<true><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
+        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
+        enc, x_bf16);
+  else
+    cast_ipe_kernel<false><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
+        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
+        enc, x_bf16);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

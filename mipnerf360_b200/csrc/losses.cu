@@ -3,6 +3,7 @@
 // reference's O(N^2) / O(N) Python loops.  Prefix sums that are later differenced are carried in fp64
 // so that the cancellation does not cost fp32 accuracy.
 #include "common.cuh"
+#include "ray_group.cuh"
 
 namespace mip360 {
 
@@ -216,6 +217,130 @@ interlevel_kernel(const float* __restrict__ w_hat, const float* __restrict__ b_p
   if (!BWD) block_sum_to_partial<256>(acc, partials);
 }
 
+// N in {32, 64, 128}: 8 lanes per ray (ray_group.cuh); the prefix sums that are differenced stay in fp64
+template <int E, bool BWD>
+__global__ void __launch_bounds__(RG_THREADS)
+distortion_rg_kernel(const float* __restrict__ s_vals, const float* __restrict__ weights, int B,
+                     float* __restrict__ per_ray, double* __restrict__ partials, const float* __restrict__ g_loss_ptr,
+                     float* __restrict__ g_w) {
+  constexpr int N = E * RG_LANES;
+  const int gl = threadIdx.x & 7, j0 = gl * E;
+  double block_acc = 0.0;
+  float g_loss = 1.f;
+  if (BWD) g_loss = *g_loss_ptr;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + (threadIdx.x >> 3);
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    float s[E + 1], w[E];
+    rg_load_knots<E>(s_vals + ray * (N + 1), j0, s);
+    rg_load<E>(weights + ray * N + j0, w);
+    double eW[E], eWM[E], runW = 0.0, runWM = 0.0;
+    float m[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      m[i] = 0.5f * (s[i] + s[i + 1]);
+      eW[i] = runW;
+      eWM[i] = runWM;
+      runW += (double)w[i];
+      runWM += (double)w[i] * (double)m[i];
+    }
+    const double offW = rg_scan_excl(runW, gl), offWM = rg_scan_excl(runWM, gl);
+    if (!BWD) {
+      double loss = 0.0;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const double Wl = offW + eW[i], WMl = offWM + eWM[i];
+        loss += 2.0 * (double)w[i] * ((double)m[i] * Wl - WMl) +
+                (double)w[i] * (double)w[i] * (double)(s[i + 1] - s[i]) / 3.0;
+      }
+      loss = rg_sum(loss);
+      if (gl == 0 && active) {
+        if (per_ray) per_ray[ray] = (float)loss;
+        block_acc += loss;
+      }
+    } else {
+      const double Wtot = __shfl_sync(FULL_MASK, offW + runW, RG_LANES - 1, RG_LANES);
+      const double WMtot = __shfl_sync(FULL_MASK, offWM + runWM, RG_LANES - 1, RG_LANES);
+      float g[E];
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const double Wl = offW + eW[i], WMl = offWM + eWM[i];
+        const double Wr = Wtot - Wl - (double)w[i], WMr = WMtot - WMl - (double)w[i] * (double)m[i];
+        const double gi = 2.0 * ((double)m[i] * (Wl - Wr) - (WMl - WMr)) +
+                          (2.0 / 3.0) * (double)w[i] * (double)(s[i + 1] - s[i]);
+        g[i] = (float)(gi * (double)g_loss);
+      }
+      if (active) rg_store<E>(g_w + ray * N + j0, g);
+    }
+  }
+  if (!BWD) block_sum_to_partial<RG_THREADS>(block_acc, partials);
+}
+
+// per-ray proposal bounds, 8 lanes per ray: fine knots + fp64 prefix weights parked in shared memory, each lane
+// resolves E coarse intervals (strided, so the group writes 8 consecutive outputs)
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
+                 int B, float* __restrict__ b_out) {
+  constexpr int N = E * RG_LANES, K = N + 1;
+  __shared__ float s_tf[RG_RAYS_PER_BLOCK][K + 3];
+  __shared__ double s_cw[RG_RAYS_PER_BLOCK][K + 1];
+  const int gl = threadIdx.x & 7, g = threadIdx.x >> 3, j0 = gl * E;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + g;
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    float tf[E + 1], w[E];
+    rg_load_knots<E>(t_fine + ray * K, j0, tf);
+    rg_load<E>(w_fine + ray * N + j0, w);
+    double run = 0.0, ex[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      ex[i] = run;
+      run += (double)w[i];
+    }
+    const double off = rg_scan_excl(run, gl);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      s_cw[g][j0 + i] = off + ex[i];
+      s_tf[g][j0 + i] = tf[i];
+    }
+    if (gl == RG_LANES - 1) {
+      s_cw[g][N] = off + run;
+      s_tf[g][N] = tf[E];
+    }
+    __syncwarp();
+    const float* tc = t_coarse + ray * K;
+#pragma unroll
+    for (int c = 0; c < E; ++c) {
+      const int i = gl + RG_LANES * c;
+      const float L = __ldg(tc + i), R = __ldg(tc + i + 1);
+      int lo = 0, hi = N;  // first j with t1_j = tf[j+1] >= L
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_tf[g][mid + 1] >= L) hi = mid; else lo = mid + 1;
+      }
+      const int first = lo;
+      lo = 0; hi = N;      // count of j with t0_j = tf[j] <= R
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_tf[g][mid] <= R) lo = mid + 1; else hi = mid;
+      }
+      const int last = lo - 1;
+      float v = 0.f;
+      if (last >= first) v = (float)(s_cw[g][last + 1] - s_cw[g][first]);
+      if (active) b_out[ray * N + i] = v;
+    }
+    __syncwarp();
+  }
+}
+
+static inline int rg_loss_grid(int B) {
+  const int g = rg_grid(B);
+  return g < LS_MAX_PARTIALS ? g : LS_MAX_PARTIALS;
+}
+
 static inline int ray_grid(int B, int warps) {
   long long b = ((long long)B + warps - 1) / warps;
   const long long cap = min((long long)sm_count() * 16, (long long)LS_MAX_PARTIALS);
@@ -238,10 +363,14 @@ int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int 
   MIP_REQUIRE(s_vals && weights && partials && loss, "distortion_fwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   MIP_REQUIRE(B >= 0, "distortion_fwd: B=%d", B);
-  const int grid = B > 0 ? ray_grid(B, LS_WARPS) : 0;
+  const bool rg = rg_supported_host(N);
+  const int grid = B > 0 ? (rg ? rg_loss_grid(B) : ray_grid(B, LS_WARPS)) : 0;
   if (grid > 0) {
-    distortion_kernel<false><<<grid, LS_WARPS * 32, 0, (cudaStream_t)stream>>>(s_vals, weights, B, N, per_ray, partials,
-                                                                                nullptr, nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 32) distortion_rg_kernel<4, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    else if (N == 64) distortion_rg_kernel<8, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    else if (N == 128) distortion_rg_kernel<16, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    else distortion_kernel<false><<<grid, LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, per_ray, partials, nullptr, nullptr);
     MIP_LAUNCH_CHECK();
   }
   reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0, loss);
@@ -254,8 +383,13 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
   MIP_REQUIRE(s_vals && weights && g_loss_ptr && g_w, "distortion_bwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  distortion_kernel<true><<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
+  {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 32) distortion_rg_kernel<4, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    else if (N == 64) distortion_rg_kernel<8, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    else if (N == 128) distortion_rg_kernel<16, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    else distortion_kernel<true><<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
+  }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -265,8 +399,13 @@ int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float*
   MIP_REQUIRE(t_fine && w_fine && t_coarse && b_out, "bounds_per_ray: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_per_ray: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, (cudaStream_t)stream>>>(t_fine, w_fine, t_coarse, B, N,
-                                                                                   b_out);
+  {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 32) bounds_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    else if (N == 64) bounds_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    else if (N == 128) bounds_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    else bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out);
+  }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

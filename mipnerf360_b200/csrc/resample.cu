@@ -4,6 +4,7 @@
 // arithmetic round like the reference's unfused ops: given the same fp32 CDF and uniforms, the bin
 // indices and samples are bit-identical to the reference's mask/max/min formulation (App. B2).
 #include "common.cuh"
+#include "ray_group.cuh"
 
 namespace mip360 {
 
@@ -179,6 +180,76 @@ invert_kernel(const float* __restrict__ bins, const float* __restrict__ cdf, con
   }
 }
 
+// N in {32, 64, 128}: 8 lanes per ray (ray_group.cuh).  Weights and knots live in registers, the blur needs one
+// neighbour value from each adjacent lane, the CDF is a lane-local loop + 3-step group scan; CDF and bins are then
+// parked in shared memory for the binary searches, and the 8 lanes write 8 consecutive samples per step.
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
+                   const float* __restrict__ jitter, int B, float padding, int blur, float* __restrict__ new_t) {
+  constexpr int N = E * RG_LANES, K = N + 1;
+  __shared__ float s_cdf[RG_RAYS_PER_BLOCK][K + 3];
+  __shared__ float s_bins[RG_RAYS_PER_BLOCK][K + 3];
+  const int gl = threadIdx.x & 7, g = threadIdx.x >> 3, j0 = gl * E;
+  const float one_m_eps = 1.f - 1.1920928955078125e-07f;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + g;
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    float w[E], t[E + 1];
+    rg_load<E>(weights + ray * N + j0, w);
+    rg_load_knots<E>(t_vals + ray * K, j0, t);
+    if (blur) {
+      float wl = __shfl_up_sync(FULL_MASK, w[E - 1], 1, RG_LANES);
+      float wr = __shfl_down_sync(FULL_MASK, w[0], 1, RG_LANES);
+      if (gl == 0) wl = w[0];
+      if (gl == RG_LANES - 1) wr = w[E - 1];
+      float mx[E + 1];  // mx[i] = max(w[j0+i-1], w[j0+i]) with replicated ends
+      mx[0] = fmaxf(wl, w[0]);
+#pragma unroll
+      for (int i = 1; i < E; ++i) mx[i] = fmaxf(w[i - 1], w[i]);
+      mx[E] = fmaxf(w[E - 1], wr);
+#pragma unroll
+      for (int i = 0; i < E; ++i) w[i] = 0.5f * (mx[i] + mx[i + 1]) + padding;
+    }
+    float loc = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) loc += w[i];
+    float wsum = rg_sum(loc);
+    const float pad = fmaxf(0.f, 1e-5f - wsum);
+    const float add = pad / (float)N;
+    wsum = wsum + pad;
+    float run = 0.f, incl[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      run += (w[i] + add) / wsum;
+      incl[i] = run;
+    }
+    const float off = rg_scan_excl(run, gl);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      s_cdf[g][j0 + i + 1] = (j0 + i == N - 1) ? 1.f : fminf(1.f, off + incl[i]);
+      s_bins[g][j0 + i] = t[i];
+    }
+    if (gl == 0) s_cdf[g][0] = 0.f;
+    if (gl == RG_LANES - 1) s_bins[g][N] = t[E];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c <= E; ++c) {
+      const int m = (c < E) ? gl + RG_LANES * c : N;
+      if (c == E && gl != 0) break;
+      float u = __ldg(u_base + m);
+      if (jitter) {
+        u = (u + u) + __ldg(jitter + ray * K + m);  // the doubled stratum offset is the reference's (App. A5)
+        u = fminf(u, one_m_eps);
+      }
+      const float x = invert_one(s_cdf[g], s_bins[g], N, u, nullptr);
+      if (active) new_t[ray * K + m] = x;
+    }
+    __syncwarp();
+  }
+}
+
 static inline int ray_grid(int B, int warps) {
   long long b = ((long long)B + warps - 1) / warps;
   const long long cap = (long long)sm_count() * 16;
@@ -227,8 +298,18 @@ int mip360_resample(const float* t_vals, const float* weights, const float* u_ba
   MIP_REQUIRE(t_vals && weights && u_base && new_t, "resample: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      t_vals, weights, u_base, jitter, B, N, resample_padding, blur, new_t);
+  if (N == 32)
+    resample_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
+                                                                              resample_padding, blur, new_t);
+  else if (N == 64)
+    resample_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
+                                                                              resample_padding, blur, new_t);
+  else if (N == 128)
+    resample_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
+                                                                               resample_padding, blur, new_t);
+  else
+    resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        t_vals, weights, u_base, jitter, B, N, resample_padding, blur, new_t);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
