@@ -249,6 +249,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
         dist.init_process_group("nccl", device_id=dev)
     from mipnerf360_b200 import _lib
     from mipnerf360_b200.model import mipNeRF360

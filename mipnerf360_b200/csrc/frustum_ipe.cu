@@ -20,6 +20,13 @@ __constant__ float c_P[21][3] = {
 
 __device__ __forceinline__ float g_disp(float x) { return 1.0f / (x + G_EPS); }  // parameterization.py:15-21
 
+// sample index -> (ray, interval) without a 64-bit division: magic = floor(2^64 / N) + 1 (host), exact for s*N < 2^64
+__device__ __forceinline__ void split_sample(long long s, int N, unsigned long long magic, int& b, int& j) {
+  b = (int)__umul64hi((unsigned long long)s, magic);
+  j = (int)(s - (long long)b * N);
+}
+static inline unsigned long long div_magic(int N) { return N > 1 ? ~0ull / (unsigned long long)N + 1ull : 0ull; }
+
 // intern/parameterization.py:101-107 (stable branch)
 __device__ __forceinline__ void frustum_moments(float t0, float t1, float radius, float& t_mean, float& t_var,
                                                 float& r_var) {
@@ -118,7 +125,7 @@ __device__ __forceinline__ void ipe_features(const float mean[3], const float co
 
 // Fast variant for the bf16 MLP rows (model path): the 21 directions are compile-time immediates (zero terms
 // vanish), sigma uses the symmetric 6-term form with FMAs, exp/sin/cos are the MUFU approximations after an
-// explicit range reduction (abs. error ~5e-7, far below the bf16 rounding of the result: 2^-9 relative).
+// (abs. error ~1e-6, far below the bf16 rounding of the result: 2^-9 relative).
 // Output: 21 packed bf16 pairs = columns 0..41 of the MLP row.
 __device__ __forceinline__ void ipe_features_bf16(const float mean[3], const float cov[9], uint32_t packed[21]) {
   constexpr float A = 0.8506508f, B = 0.5257311f, C = 0.809017f, D = 0.5f, E = 0.309017f;
@@ -141,10 +148,10 @@ __device__ __forceinline__ void ipe_features_bf16(const float mean[3], const flo
     if (p0 * p2 != 0.f) sigma = fmaf(p0 * p2, c02, sigma);
     if (p1 * p2 != 0.f) sigma = fmaf(p1 * p2, c12, sigma);
     const float damp = exp2f(-0.72134752f * sigma);  // exp(-sigma/2) = 2^(-sigma/(2 ln 2)): one MUFU.EX2
-    const float kf = rintf(gamma * 0.15915494f);      // range reduction to [-pi, pi]
-    const float r = fmaf(kf, -6.2831855f, gamma);
-    sn[k] = damp * __sinf(r);
-    cs[k] = damp * __cosf(r);
+    // MUFU.SIN/COS reduce the argument themselves; |gamma| stays O(scene radius), where their absolute error
+    // (~|gamma| * 2^-22) is far below the bf16 rounding of the product
+    sn[k] = damp * __sinf(gamma);
+    cs[k] = damp * __cosf(gamma);
   }
 #pragma unroll
   for (int c = 0; c < 10; ++c) packed[c] = pack_bf16x2(sn[2 * c], sn[2 * c + 1]);
@@ -177,7 +184,8 @@ __global__ void __launch_bounds__(K1_THREADS)
 cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
                 const float* __restrict__ origins, const float* __restrict__ directions,
                 const float* __restrict__ vdir_enc, const float* __restrict__ radii,
-                const double* __restrict__ norm_sq, long long S, int N, int contract_mode, int add_origins,
+                const double* __restrict__ norm_sq, long long S, int N, unsigned long long magic, int contract_mode,
+                int add_origins,
                 float* __restrict__ means_out, float* __restrict__ covs_out, float* __restrict__ enc_out,
                 uint16_t* __restrict__ x_out) {
   __shared__ __align__(16) float stage_all[(K1_THREADS / 32) * K1_STAGE_FLOATS];
@@ -189,8 +197,8 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
   const bool valid = s < S;
   const int rows_valid = (int)min((long long)32, S - warp_s0);
   const long long sc = valid ? s : S - 1;
-  const int b = (int)(sc / N);
-  const int j = (int)(sc - (long long)b * N);
+  int b, j;
+  if (N > 1) split_sample(sc, N, magic, b, j); else { b = (int)sc; j = 0; }
 
   float n_global = 0.f;
   if (contract_mode == 0) n_global = (float)sqrt(*norm_sq);
@@ -271,18 +279,21 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
 // accumulated in fp64.
 __global__ void __launch_bounds__(256)
 frustum_norm_sq_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
-                       const float* __restrict__ directions, long long S, int N, double* __restrict__ out) {
+                       const float* __restrict__ directions, long long S, int N, unsigned long long magic,
+                       double* __restrict__ out) {
   double acc = 0.0;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(s / N);
-    const int j = (int)(s - (long long)b * N);
+    int b, j;
+    if (N > 1) split_sample(s, N, magic, b, j); else { b = (int)s; j = 0; }
     const float t0 = t0p[(long long)b * t_stride + j], t1 = t1p[(long long)b * t_stride + j];
-    float t_mean, t_var, r_var;
-    frustum_moments(t0, t1, 0.f, t_mean, t_var, r_var);
+    // t_mean of parameterization.py:103 only (t_var / r_var are not needed here)
+    const float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
+    const float hw2 = hw * hw;
+    const float t_mean = mu + (2.f * mu * hw2) / (3.f * (mu * mu) + hw2);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const float m = directions[b * 3 + i] * t_mean;
-      acc += (double)m * (double)m;
+      acc += (double)(m * m);
     }
   }
   acc = warp_sum(acc);
@@ -452,7 +463,7 @@ int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
   frustum_norm_sq_kernel<<<capped_blocks(S, 256), 256, 0, (cudaStream_t)stream>>>(t0, t1, t_stride, directions, S, N,
-                                                                                  norm_sq);
+                                                                                  div_magic(N), norm_sq);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -470,12 +481,12 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
   const long long S = (long long)B * N;
   if (x_bf16 && !means && !covs && !enc)
     cast_ipe_kernel<true><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
-        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
-        enc, x_bf16);
+        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, div_magic(N), contract_mode, add_origins,
+        means, covs, enc, x_bf16);
   else
     cast_ipe_kernel<false><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
-        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, contract_mode, add_origins, means, covs,
-        enc, x_bf16);
+        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, div_magic(N), contract_mode, add_origins,
+        means, covs, enc, x_bf16);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -247,14 +247,16 @@ distortion_rg_kernel(const float* __restrict__ s_vals, const float* __restrict__
     }
     const double offW = rg_scan_excl(runW, gl), offWM = rg_scan_excl(runWM, gl);
     if (!BWD) {
+      // the pair term is a difference of prefix sums (fp64); the self term is a plain positive sum (fp32)
       double loss = 0.0;
+      float self = 0.f;
 #pragma unroll
       for (int i = 0; i < E; ++i) {
         const double Wl = offW + eW[i], WMl = offWM + eWM[i];
-        loss += 2.0 * (double)w[i] * ((double)m[i] * Wl - WMl) +
-                (double)w[i] * (double)w[i] * (double)(s[i + 1] - s[i]) / 3.0;
+        loss += (double)w[i] * ((double)m[i] * Wl - WMl);
+        self += (w[i] * w[i]) * (s[i + 1] - s[i]);
       }
-      loss = rg_sum(loss);
+      loss = rg_sum(2.0 * loss + (double)self * (1.0 / 3.0));
       if (gl == 0 && active) {
         if (per_ray) per_ray[ray] = (float)loss;
         block_acc += loss;
@@ -312,25 +314,34 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     }
     __syncwarp();
     const float* tc = t_coarse + ray * K;
+    // branch-free counting searches, the lane's E intervals in lock step:
+    //   first = #{j < N : t1_j = tf[j+1] < L}   (= first j with t1_j >= L),   nR = #{j < N : t0_j = tf[j] <= R}
+    float L[E], R[E];
+    int first[E], nR[E];
 #pragma unroll
     for (int c = 0; c < E; ++c) {
       const int i = gl + RG_LANES * c;
-      const float L = __ldg(tc + i), R = __ldg(tc + i + 1);
-      int lo = 0, hi = N;  // first j with t1_j = tf[j+1] >= L
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_tf[g][mid + 1] >= L) hi = mid; else lo = mid + 1;
+      L[c] = __ldg(tc + i);
+      R[c] = __ldg(tc + i + 1);
+      first[c] = 0;
+      nR[c] = 0;
+    }
+#pragma unroll
+    for (int step = N; step > 0; step >>= 1) {
+#pragma unroll
+      for (int c = 0; c < E; ++c) {
+        const int pf = first[c] + step, pr = nR[c] + step;
+        const float vf = s_tf[g][min(pf, N)];      // tf[(pf-1)+1]
+        const float vr = s_tf[g][min(pr, N) - 1];  // tf[pr-1]
+        if (pf <= N && vf < L[c]) first[c] = pf;
+        if (pr <= N && vr <= R[c]) nR[c] = pr;
       }
-      const int first = lo;
-      lo = 0; hi = N;      // count of j with t0_j = tf[j] <= R
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_tf[g][mid] <= R) lo = mid + 1; else hi = mid;
-      }
-      const int last = lo - 1;
+    }
+#pragma unroll
+    for (int c = 0; c < E; ++c) {
       float v = 0.f;
-      if (last >= first) v = (float)(s_cw[g][last + 1] - s_cw[g][first]);
-      if (active) b_out[ray * N + i] = v;
+      if (nR[c] - 1 >= first[c]) v = (float)(s_cw[g][nR[c]] - s_cw[g][first[c]]);
+      if (active) b_out[ray * N + gl + RG_LANES * c] = v;
     }
     __syncwarp();
   }

@@ -234,17 +234,43 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
     if (gl == 0) s_cdf[g][0] = 0.f;
     if (gl == RG_LANES - 1) s_bins[g][N] = t[E];
     __syncwarp();
+    // the lane's E searches advance in lock step (branch-free counting search): log2(N)+1 dependent shared-memory
+    // reads in total instead of per sample.  cnt = number of knots <= u, i.e. upper_bound.
+    float u[E];
+    int cnt[E];
 #pragma unroll
-    for (int c = 0; c <= E; ++c) {
-      const int m = (c < E) ? gl + RG_LANES * c : N;
-      if (c == E && gl != 0) break;
-      float u = __ldg(u_base + m);
+    for (int c = 0; c < E; ++c) {
+      const int m = gl + RG_LANES * c;
+      u[c] = __ldg(u_base + m);
       if (jitter) {
-        u = (u + u) + __ldg(jitter + ray * K + m);  // the doubled stratum offset is the reference's (App. A5)
-        u = fminf(u, one_m_eps);
+        u[c] = (u[c] + u[c]) + __ldg(jitter + ray * K + m);  // the doubled stratum offset is the reference's (App. A5)
+        u[c] = fminf(u[c], one_m_eps);
       }
-      const float x = invert_one(s_cdf[g], s_bins[g], N, u, nullptr);
-      if (active) new_t[ray * K + m] = x;
+      cnt[c] = 0;
+    }
+#pragma unroll
+    for (int step = N; step > 0; step >>= 1) {
+#pragma unroll
+      for (int c = 0; c < E; ++c) {
+        const int probe = cnt[c] + step;
+        const float v = s_cdf[g][min(probe, K) - 1];
+        if (probe <= K && v <= u[c]) cnt[c] = probe;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < E; ++c) {
+      const int i0 = max(cnt[c] - 1, 0), i1 = min(cnt[c], N);
+      const float c0 = s_cdf[g][i0], c1 = s_cdf[g][i1];
+      const float b0 = s_bins[g][i0], b1 = s_bins[g][i1];
+      float tt = nan_to_num_f((u[c] - c0) / (c1 - c0), 0.f);
+      tt = fminf(fmaxf(tt, 0.f), 1.f);
+      if (active) new_t[ray * K + gl + RG_LANES * c] = b0 + tt * (b1 - b0);
+    }
+    if (gl == 0) {  // sample N (the (N+1)-th): one per ray
+      float un = __ldg(u_base + N);
+      if (jitter) un = fminf((un + un) + __ldg(jitter + ray * K + N), one_m_eps);
+      const float x = invert_one(s_cdf[g], s_bins[g], N, un, nullptr);
+      if (active) new_t[ray * K + N] = x;
     }
     __syncwarp();
   }

@@ -153,8 +153,18 @@ def look_at(eye, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)):
 
 
 def render(out_path, chunks):
+    """Under torchrun every rank renders its slab of the image (ray partition) and the result is all-gathered."""
+    import torch.distributed as dist
+    global DEV
     from mipnerf360_b200.model import mipNeRF360
     from mipnerf360_b200.render import render_image_distributed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        DEV = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=DEV)
     torch.manual_seed(0)
     model = mipNeRF360(randomized=False, num_samples=64, device=DEV)
     res = []
@@ -165,20 +175,29 @@ def render(out_path, chunks):
         n = h * w
         render_image_distributed(model, Rays(*[r[: 4 * chunks] for r in rays]), 1, min(n, 4 * chunks), chunks)  # warm-up
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rgb, d, a = render_image_distributed(model, rays, h, w, chunks)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms_t = torch.tensor([e0.elapsed_time(e1)], device=DEV, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        ms = float(ms_t)
         flop = n * 64 * 2 * (58 * 256 + 3 * 256 * 256 + 256 + 58 * 1024 + 7 * 1024 * 1024 + 4 * 1024)
-        row = dict(case=name, rays=n, chunks=chunks, ms=ms, rays_per_s=n / (ms * 1e-3), tflops=flop / (ms * 1e-3) / 1e12,
+        row = dict(case=name, n_gpus=world, rays=n, chunks=chunks, ms=ms, rays_per_s=n / (ms * 1e-3), tflops=flop / (ms * 1e-3) / 1e12,
                    finite=bool(torch.isfinite(rgb).all()), mean_acc=float(a.mean()))
-        print(row, flush=True)
+        if rank == 0:
+            print(row, flush=True)
         res.append(row)
         del rays, rgb, d, a
         torch.cuda.empty_cache()
-    json.dump(dict(rows=res), open(out_path, "w"), indent=1)
+    if rank == 0:
+        json.dump(dict(rows=res), open(out_path, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
