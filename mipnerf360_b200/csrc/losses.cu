@@ -169,7 +169,7 @@ bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine
       }
       const int last = lo - 1;
       float v = 0.f;
-      if (last >= first) v = (float)(s.cumw[last + 1] - s.cumw[first]);
+      if (last >= first) v = fmaxf((float)(s.cumw[last + 1] - s.cumw[first]), 0.f);
       b_out[(long long)b * N + i] = v;
     }
     __syncwarp();
@@ -340,7 +340,7 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
 #pragma unroll
     for (int c = 0; c < E; ++c) {
       float v = 0.f;
-      if (nR[c] - 1 >= first[c]) v = (float)(s_cw[g][nR[c]] - s_cw[g][first[c]]);
+      if (nR[c] - 1 >= first[c]) v = fmaxf((float)(s_cw[g][nR[c]] - s_cw[g][first[c]]), 0.f);
       if (active) b_out[ray * N + gl + RG_LANES * c] = v;
     }
     __syncwarp();

@@ -54,10 +54,21 @@ __device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int 
   }
   const float incl = warp_scan_incl(run, lane);
   const float off = incl - run;
+  // The tree scan can leave a lane's offset one ulp below the last value of the lane before it.  A CDF must be
+  // non-decreasing (the search relies on it), so every value is raised to the running maximum of the preceding
+  // lanes' last values; max is exact and associative, so this is a plain shuffle scan.
+  float pm = off + run;  // this lane's last value
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(FULL_MASK, pm, o);
+    if (lane >= o) pm = fmaxf(pm, n);
+  }
+  pm = __shfl_up_sync(FULL_MASK, pm, 1);
+  if (lane == 0) pm = 0.f;
 #pragma unroll
   for (int c = 0; c < (MIP360_MAX_SAMPLES + 31) / 32; ++c) {
     const int j = j0 + c;
-    if (c < C && j < N - 1) cdf[j + 1] = fminf(1.f, off + pdf_loc[c]);
+    if (c < C && j < N - 1) cdf[j + 1] = fminf(1.f, fmaxf(off + pdf_loc[c], pm));
   }
   if (lane == 0) {
     cdf[0] = 0.f;
@@ -226,9 +237,18 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
       incl[i] = run;
     }
     const float off = rg_scan_excl(run, gl);
+    // keep the CDF non-decreasing across lane boundaries (see warp_cdf): exact running max of the lanes' last values
+    float pm = off + run;
+#pragma unroll
+    for (int o = 1; o < RG_LANES; o <<= 1) {
+      const float n = __shfl_up_sync(FULL_MASK, pm, o, RG_LANES);
+      if (gl >= o) pm = fmaxf(pm, n);
+    }
+    pm = __shfl_up_sync(FULL_MASK, pm, 1, RG_LANES);
+    if (gl == 0) pm = 0.f;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      s_cdf[g][j0 + i + 1] = (j0 + i == N - 1) ? 1.f : fminf(1.f, off + incl[i]);
+      s_cdf[g][j0 + i + 1] = (j0 + i == N - 1) ? 1.f : fminf(1.f, fmaxf(off + incl[i], pm));
       s_bins[g][j0 + i] = t[i];
     }
     if (gl == 0) s_cdf[g][0] = 0.f;

@@ -1,0 +1,155 @@
+"""Size-independent properties at the BASELINE.json sizes (16 384 rays x 64 samples per call; 65 536-ray render
+chunks) where the CPU oracle would take minutes: sortedness, conservation, scaling laws, exact special cases,
+and a short training run through the public Trainer."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, N = 16384, 64
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mipnerf360_b200 import ops as _ops
+    return _ops
+
+
+def _rays(b, seed=0):
+    from mipnerf360_b200.intern.ray import Rays
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    o = torch.randn(b, 3, device=DEV, generator=g)
+    d = torch.randn(b, 3, device=DEV, generator=g)
+    return Rays(o, d, d / d.norm(dim=-1, keepdim=True), torch.full((b, 1), 1e-3, device=DEV),
+                torch.full((b, 1), 0.1, device=DEV), torch.full((b, 1), 10.0, device=DEV))
+
+
+def test_resample_properties_full_size(ops):
+    g = torch.Generator(device=DEV).manual_seed(1)
+    t = (torch.rand(B, N + 1, device=DEV, generator=g) * 0.3).cumsum(-1) + 0.1
+    w = torch.rand(B, N, device=DEV, generator=g) ** 4
+    jit = ops.draw_jitter(B, N + 1, DEV)
+    for randomized in (False, True):
+        s = ops.resample(t, w, randomized, 0.01, jitter=jit)
+        assert torch.isfinite(s).all()
+        assert (s[:, 1:] >= s[:, :-1]).all(), "samples must be sorted"
+        assert (s >= t[:, :1]).all() and (s <= t[:, -1:]).all(), "samples stay inside the bins"
+        # the pdf is normalised: a positive rescaling of the weights leaves the samples unchanged (no padding, no blur)
+        a = ops.resample(t, w + 1e-3, randomized, 0.0, jitter=jit, blur=False)
+        b = ops.resample(t, 8.0 * (w + 1e-3), randomized, 0.0, jitter=jit, blur=False)  # power of two: exact pdf
+        assert torch.equal(a, b)
+    # uniform weights + deterministic u = linspace: the samples reproduce a uniform grid's own knots
+    tu = torch.linspace(1.0, 3.0, N + 1, device=DEV).expand(64, N + 1).contiguous()
+    s = ops.resample(tu, torch.ones(64, N, device=DEV), False, 0.0, blur=False)
+    torch.testing.assert_close(s[:, :-1], tu[:, :-1], rtol=1e-5, atol=1e-5)
+    # two-stage API at full size: indices in range and consistent with the cdf
+    cdf = ops.resample_cdf(w)
+    assert (cdf[:, 1:] >= cdf[:, :-1]).all() and (cdf[:, 0] == 0).all() and (cdf[:, -1] == 1).all()
+    u = torch.rand(B, N + 1, device=DEV, generator=g)
+    smp, idx = ops.resample_invert(t, cdf, u, return_idx=True)
+    idx = idx.long()
+    assert (idx >= 0).all() and (idx <= N).all()
+    assert (torch.gather(cdf, 1, idx) <= u).all()
+    nxt = torch.gather(cdf, 1, (idx + 1).clamp(max=N))
+    assert ((nxt > u) | (idx == N)).all()
+
+
+def test_compositing_properties_full_size(ops):
+    g = torch.Generator(device=DEV).manual_seed(2)
+    t = (torch.rand(B, N + 1, device=DEV, generator=g) * 0.3).cumsum(-1) + 0.1
+    dens = torch.rand(B, N, 1, device=DEV, generator=g) * 4
+    dirs = torch.randn(B, 3, device=DEV, generator=g)
+    colour = torch.rand(3, device=DEV, generator=g)
+    rgb = colour.expand(B, N, 3).contiguous()
+    comp, dist, acc, w = ops.composite(rgb, dens, t, dirs, False)
+    assert (w >= 0).all() and (acc <= 1 + 1e-5).all()
+    torch.testing.assert_close(acc, w.sum(-1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(comp, acc[:, None] * colour, rtol=1e-5, atol=1e-6)  # constant colour composites to c*acc
+    assert (dist >= t[:, 0]).all() and (dist <= t[:, -1]).all()
+    comp_w, _, acc_w, _ = ops.composite(rgb, dens, t, dirs, True)
+    torch.testing.assert_close(comp_w, acc[:, None] * colour + (1 - acc)[:, None], rtol=1e-5, atol=1e-6)
+    # weights = alpha * transmittance  =>  1 - sum(w) = exp(-sum(sigma*delta)) (telescoping product)
+    delta = (t[:, 1:] - t[:, :-1]) * dirs.norm(dim=-1, keepdim=True)
+    torch.testing.assert_close(1 - acc, torch.exp(-(dens[..., 0] * delta).sum(-1)), rtol=1e-4, atol=1e-5)
+    # weights-only path agrees with the full path
+    torch.testing.assert_close(ops.density_to_weight(t, dens, dirs), w, rtol=0, atol=0)
+
+
+def test_loss_properties_full_size(ops):
+    g = torch.Generator(device=DEV).manual_seed(3)
+    s = torch.rand(B, N + 1, device=DEV, generator=g).cumsum(-1)
+    s = s / s[:, -1:]
+    w = torch.rand(B, N, device=DEV, generator=g) * (2.0 / N)
+    base = ops.distortion_loss(s, w)
+    assert torch.isfinite(base) and base > 0
+    torch.testing.assert_close(ops.distortion_loss(s, 3 * w), 9 * base, rtol=1e-5, atol=0)   # quadratic in w
+    perm = torch.randperm(B, device=DEV, generator=g)
+    torch.testing.assert_close(ops.distortion_loss(s[perm], w[perm]), base, rtol=1e-6, atol=0)  # sum over rays
+    torch.testing.assert_close(ops.distortion_per_ray(s, w).double().sum().float(), base, rtol=1e-6, atol=0)
+    one_hot = torch.zeros(8, N, device=DEV)
+    one_hot[:, 5] = 1.0  # a single interval: only the self term w^2 ds / 3 remains
+    torch.testing.assert_close(ops.distortion_per_ray(s[:8], one_hot), (s[:8, 6] - s[:8, 5]) / 3, rtol=1e-5, atol=1e-8)
+    # interlevel: identical grids -> each interval overlaps itself and both neighbours (closed intervals)
+    t = (torch.rand(B, N + 1, device=DEV, generator=g) * 0.3 + 0.01).cumsum(-1)
+    b = ops.bounds_per_ray(t, w, t)
+    pad = torch.nn.functional.pad(w, (1, 1))
+    torch.testing.assert_close(b, pad[:, :-2] + pad[:, 1:-1] + pad[:, 2:], rtol=1e-5, atol=1e-7)
+    tot = ops.bounds_total(b)
+    torch.testing.assert_close(tot, b.double().sum(0), rtol=1e-9, atol=0)
+    # an envelope (w_hat >= bound everywhere) costs nothing and has zero gradient
+    w_hat = (tot.float()[None, :].expand(B, N) + 1e-3).clone().requires_grad_(True)
+    loss = ops.interlevel_loss(w_hat, bound_total=tot)
+    assert float(loss) == 0.0
+    loss.backward()
+    assert (w_hat.grad == 0).all()
+
+
+def test_encoding_properties_full_size(ops):
+    rays = _rays(B, 4)
+    t = ops.level0_t_vals(rays.near, rays.far, N, True)
+    assert (t[:, 1:] >= t[:, :-1]).all() and (t > 0).all()
+    vd = ops.viewdir_enc(rays.viewdirs)
+    torch.testing.assert_close(vd[:, :4] ** 2 + vd[:, 4:8] ** 2, torch.ones(B, 4, device=DEV), rtol=1e-5, atol=1e-6)
+    out = ops.cast_ipe(t, rays.origins, rays.directions, rays.radii, vd, want_enc=True, want_x=True, want_covs=True)
+    enc = out["enc"]
+    amp2 = enc[..., :21] ** 2 + enc[..., 21:] ** 2  # = exp(-sigma) <= 1 for a PSD covariance
+    assert (amp2 <= 1 + 1e-5).all() and torch.isfinite(enc).all()
+    cov = out["covs"]
+    assert (torch.diagonal(cov, dim1=-2, dim2=-1) >= -1e-12).all()
+    x = out["x"].float().view(B, N, 64)
+    torch.testing.assert_close(x[..., :42], enc, rtol=2 ** -7, atol=2 ** -8)     # bf16 rows carry the same features
+    torch.testing.assert_close(x[..., 42:58], vd[:, None, :].expand(B, N, 16), rtol=2 ** -7, atol=2 ** -8)
+    assert (x[..., 58:] == 0).all()
+    # fast (bf16-only) and exact variants of the kernel agree to bf16 rounding
+    x_fast = ops.cast_ipe(t, rays.origins, rays.directions, rays.radii, vd, norm_sq=out["norm_sq"], want_x=True)["x"]
+    torch.testing.assert_close(x_fast.float().view(B, N, 64), x, rtol=2 ** -6, atol=2 ** -7)
+
+
+def test_model_and_trainer_full_size():
+    from mipnerf360_b200 import _lib
+    from mipnerf360_b200.model import mipNeRF360
+    from mipnerf360_b200.train import Trainer
+    torch.manual_seed(0)
+    m = mipNeRF360(randomized=True, num_samples=N, device=torch.device(DEV))
+    rays = _rays(B, 5)
+    with torch.no_grad():
+        rgb, dist, acc = m(rays)
+    assert rgb.shape == (B, 3) and torch.isfinite(rgb).all() and torch.isfinite(dist).all()
+    assert (acc >= 0).all() and (acc <= 1 + 1e-4).all()
+    assert (rgb >= -0.002).all() and (rgb <= 1.002).all()
+    # a short optimisation on a fixed batch through the fused trainer: finite, and the photometric loss goes down
+    small = type(rays)(*[r[:4096] for r in rays])
+    pixels = torch.rand(4096, 3, device=DEV)
+    tr = Trainer(m, lr_delay_steps=0)
+    _lib.reset_launch_count()
+    losses = [float(tr.step(small, pixels)[1]) for _ in range(8)]
+    assert all(torch.isfinite(torch.tensor(losses)))
+    # (the very first Adam step moves all 7.6 M weights by +-lr and the loss jumps; from there it must go down)
+    assert min(losses[4:]) < losses[1], losses
+    assert _lib.launch_count() > 8 * 100
+    # checkpoint round trip through the reference's state_dict layout (flat-buffer views included)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m2 = mipNeRF360(randomized=True, num_samples=N, device=torch.device(DEV))
+    m2.load_state_dict(sd)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
