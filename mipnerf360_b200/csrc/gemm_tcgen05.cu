@@ -28,15 +28,18 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_SIGMOID_FAST = 3 /* inte
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
 // each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB (6 stages
 // instead of 4 in the same shared memory) and B is fetched from L2 once per pair.
-template <int BN, int CG = 1>
+// OCC = 2 ("short-K" configuration): BN = 128 tiles, 2 smem stages, two CTAs co-resident per SM.  Layers with a
+// short reduction (K <= 256: the 58-wide input layers, the 256-wide proposal net, the head dgrad) are bound by
+// the epilogue, not the MMAs; two resident CTAs double the number of epilogue warps per SM.
+template <int BN, int CG = 1, int OCC = 1>
 struct LinearCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? (CG == 1 ? 4 : 5) : (BN >= 128 ? 5 : 6);
+  static constexpr int STAGES = OCC == 2 ? 2 : (BN >= 256) ? (CG == 1 ? 4 : 5) : (BN >= 128 ? 5 : 6);
   // epilogue boxes per warp: 3 when shared memory allows (the saved-activation box of dgrad is then
   // prefetched a whole chunk ahead), else 2
-  static constexpr int NBOX = (BN >= 256 && CG == 1) ? 2 : 3;
+  static constexpr int NBOX = ((BN >= 256 && CG == 1) || OCC == 2) ? 2 : 3;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two >= 32)
   // epilogue staging: per epilogue warp one 4 KB [32 rows x 64 cols] bf16 box for the TMA store, and a second
   // region of the same size that holds the saved-activation box (dgrad) or, shared by all warps, the bias
@@ -44,7 +47,8 @@ struct LinearCfg {
   static constexpr int EPI_BOX_BYTES = 32 * 64 * 2;
   static constexpr int EPI_BYTES = NBOX * 4 * EPI_BOX_BYTES + 1024 /* bias tile: up to 256 floats */;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;  static_assert(SMEM_BYTES <= 232448 / OCC, "exceeds the shared memory available per CTA at this occupancy");
+  static_assert(TMEM_COLS * OCC <= 512, "tensor memory oversubscribed");
 };
 
 struct LinearParams {
@@ -111,12 +115,12 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, int CG, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC)
 linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_y,
               const LinearParams p) {
-  using Cfg = LinearCfg<BN, CG>;
+  using Cfg = LinearCfg<BN, CG, OCC>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
@@ -588,13 +592,14 @@ static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long lon
   return MIP360_OK;
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int OCC = 1>
 static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
                          cudaStream_t stream) {
-  using Cfg = LinearCfg<BN, CG>;
+  using Cfg = LinearCfg<BN, CG, OCC>;
   static bool configured = false;
   if (!configured) {
-    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
     configured = true;
   }
   CUtensorMap ta, tb, tout, ty;
@@ -606,10 +611,10 @@ static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* 
   if (p.out_bf16 && (rc = make_tmap(&tout, p.out_bf16, p.M, p.N, 32)) != MIP360_OK) return rc;
   if (EPI == EPI_DGRAD && (rc = make_tmap(&ty, yprev, p.M, p.N, 32)) != MIP360_OK) return rc;
   const int tiles = ((p.M + BM * CG - 1) / (BM * CG)) * (p.N / BN);
-  const int units = sm_count() / CG;
+  const int units = sm_count() * OCC / CG;
   const int grid = (tiles < units ? tiles : units) * CG;
   if (CG == 1) {
-    linear_kernel<BN, EPI, CG><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
+    linear_kernel<BN, EPI, CG, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -623,7 +628,7 @@ static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MIP_CUDA(cudaLaunchKernelEx(&cfg, linear_kernel<BN, EPI, CG>, ta, tb, tout, ty, p));
+    MIP_CUDA(cudaLaunchKernelEx(&cfg, linear_kernel<BN, EPI, CG, OCC>, ta, tb, tout, ty, p));
   }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
@@ -636,6 +641,9 @@ static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t
   static const bool pair_ok = getenv("MIP360_NO_CTA_PAIR") == nullptr;
   if (p.N % 256 == 0 && p.K >= 512 && pair_ok && p.M >= 256 * (sm_count() / 2))
     return launch_linear<256, EPI, 2>(A, Bw, yprev, p, stream);
+  static const bool short_ok = getenv("MIP360_NO_SHORTK") == nullptr;
+  if (p.N % 128 == 0 && p.K <= (EPI == EPI_DGRAD ? 256 : 128) && short_ok && p.M >= 128 * sm_count())
+    return launch_linear<128, EPI, 1, 2>(A, Bw, yprev, p, stream);
   if (p.N % 256 == 0) return launch_linear<256, EPI, 1>(A, Bw, yprev, p, stream);
   if (p.N == 128) return launch_linear<128, EPI, 1>(A, Bw, yprev, p, stream);
   if (p.N == 64) return launch_linear<64, EPI, 1>(A, Bw, yprev, p, stream);
