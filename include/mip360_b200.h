@@ -205,6 +205,18 @@ int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_
 /* number of SMs the persistent GEMM grids are sized for (148 on B200) */
 int mip360_sm_count(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Ray generation on the device (SURVEY §8f rank 1 — the step immediately before the hot path)
+ *   dataset.py:109-145 (pinhole camera model, radii from the row-neighbour direction distance) and, with
+ *   ndc = 1, dataset.py:364-387 + intern/ray.py:59-79 (NDC origins/directions at plane ndc_near, radii from
+ *   both NDC-origin neighbours).  c2w [n_img, c2w_rows >= 3, 4] row-major camera-to-world matrices.
+ *   Outputs are flattened like dataset.py:147-152: ray index = (img*H + y)*W + x; origins, directions,
+ *   viewdirs [n,3]; radii, near, far [n,1].
+ * ------------------------------------------------------------------------------------------ */
+int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal, float near, float far,
+                         int ndc, float ndc_near, float* origins, float* directions, float* viewdirs, float* radii,
+                         float* near_out, float* far_out, mip360_stream_t stream);
+
 /* fused AdamW over one flat fp32 parameter tensor (train.py:38,63,81 — "next" row f3 of SURVEY §8):
  * decoupled weight decay, bias correction from `step` (1-based), optional bf16 re-cast of the weights */
 int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mip360_linear_dgrad": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "mip360_linear_wgrad": [P, P, c_int, c_int, c_int, P, P, P],
     "mip360_cast_weight": [P, c_int, c_int, c_int, c_int, P, P, P],
+    "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
     "mip360_adamw": [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P],
 }
 _RESTYPES = {

@@ -23,6 +23,7 @@ SOURCES = {
     "resample.cu": ["--fmad=false"],
     "composite.cu": ["--fmad=false"],
     "losses.cu": ["--fmad=false"],
+    "raygen.cu": ["--fmad=false"],
     "gemm_tcgen05.cu": [],
 }
 

@@ -282,8 +282,10 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
       const int i0 = max(cnt[c] - 1, 0), i1 = min(cnt[c], N);
       const float c0 = s_cdf[g][i0], c1 = s_cdf[g][i1];
       const float b0 = s_bins[g][i0], b1 = s_bins[g][i1];
-      float tt = nan_to_num_f((u[c] - c0) / (c1 - c0), 0.f);
-      tt = fminf(fmaxf(tt, 0.f), 1.f);
+      // clip(nan_to_num((u-c0)/(c1-c0), 0), 0, 1) without the special-value tests: a zero-width CDF step gives
+      // +inf -> 1 when u > c0 and nan -> 0 when u == c0 (c0 <= u always holds for the selected knot)
+      const float den = c1 - c0, num = u[c] - c0;
+      const float tt = den > 0.f ? fminf(fmaxf(num / den, 0.f), 1.f) : (num > 0.f ? 1.f : 0.f);
       if (active) new_t[ray * K + gl + RG_LANES * c] = b0 + tt * (b1 - b0);
     }
     if (gl == 0) {  // sample N (the (N+1)-th): one per ray

@@ -479,3 +479,22 @@ def head_grad_pack(g, y, act):
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     call("mip360_adamw", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
          float(weight_decay), int(step))
+
+
+# ------------------------------------------------------------------------------------------------
+# ray generation
+# ------------------------------------------------------------------------------------------------
+def generate_rays(cam_to_world, h, w, focal, near, far, ndc=False, ndc_near=1.0):
+    """dataset.py:109-145 (pinhole) / dataset.py:364-387 (LLFF NDC), flattened as dataset.py:147-152.
+    cam_to_world [n, >=3, 4] device tensor -> Rays of [n*h*w, c] device tensors; nothing is built on the host."""
+    from mipnerf360_b200.intern.ray import Rays
+    c2w = f32c(cam_to_world)
+    check_cuda(c2w)
+    if c2w.dim() == 2:
+        c2w = c2w[None]
+    n = c2w.shape[0] * h * w
+    o, d, v = _empty((n, 3), c2w), _empty((n, 3), c2w), _empty((n, 3), c2w)
+    r, nr, fr = _empty((n, 1), c2w), _empty((n, 1), c2w), _empty((n, 1), c2w)
+    call("mip360_generate_rays", ptr(c2w), c2w.shape[1], c2w.shape[0], int(h), int(w), float(focal), float(near),
+         float(far), int(bool(ndc)), float(ndc_near), ptr(o), ptr(d), ptr(v), ptr(r), ptr(nr), ptr(fr))
+    return Rays(o, d, v, r, nr, fr)

@@ -171,7 +171,8 @@ def render(out_path, chunks):
     cases = [("llff_1008x756_ndc", 756, 1008, 0.82 * 1008, torch.eye(4, device=DEV), 0.05, 1.0, True),
              ("garden_4946x3286_unbounded", 3286, 4946, 0.8 * 4946, look_at((4.0, 0.0, 1.5)), 0.2, 1e3, False)]
     for name, h, w, focal, c2w, near, far, ndc in cases:
-        rays = pinhole_rays(h, w, focal, c2w, near, far, ndc)
+        # rays come from the device generator (mip360_generate_rays): nothing is built or uploaded by the host
+        rays = ops.generate_rays(c2w.to(DEV), h, w, focal, near, far, ndc=ndc)
         n = h * w
         render_image_distributed(model, Rays(*[r[: 4 * chunks] for r in rays]), 1, min(n, 4 * chunks), chunks)  # warm-up
         torch.cuda.synchronize()

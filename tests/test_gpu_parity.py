@@ -571,3 +571,32 @@ def test_render_image_distributed_single_rank():
     close(dist, torch.from_numpy(dist2), atol=0)
     close(acc, torch.from_numpy(acc2), atol=0)
     assert (torch.from_numpy(img).float() - (rgb.clamp(0, 1) * 255).cpu().floor()).abs().max() <= 1
+
+
+def test_ray_generation_vs_reference_and_oracle(ops):
+    """mip360_generate_rays against the literal reference generators (golden) and the NumPy oracle at a larger size."""
+    import os
+    import numpy as np
+    from oracle import raygen_oracle as R
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "raygen_golden.npz"))
+    for tag, ndc in (("pinhole", False), ("pinhole_wide", False), ("llff_ndc", True)):
+        h, w, focal, near, far = z[tag + "/hwf"]
+        rays = ops.generate_rays(torch.from_numpy(z[tag + "/c2w"]).to(DEV), int(h), int(w), float(focal), float(near),
+                                 float(far), ndc=ndc)
+        for k in rays._fields:
+            ref = torch.from_numpy(np.asarray(z[f"{tag}/{k}"], dtype=np.float32)).reshape(-1, z[f"{tag}/{k}"].shape[-1])
+            close(getattr(rays, k), ref, rtol=1e-5, atol=1e-6 * float(ref.abs().max()), msg=f"{tag} {k}")
+    rng = np.random.default_rng(1)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    c2w = np.concatenate([q, rng.normal(size=(3, 1))], 1).astype(np.float32)[None]
+    h, w, focal = 189, 252, 0.82 * 252
+    ref = R.flatten(R.pinhole_rays(c2w, h, w, focal, 0.1, 10.0))
+    rays = ops.generate_rays(torch.from_numpy(c2w).to(DEV), h, w, focal, 0.1, 10.0)
+    for k in rays._fields:
+        close(getattr(rays, k), torch.from_numpy(ref[k]), rtol=1e-5, atol=1e-6 * float(np.abs(ref[k]).max()), msg=k)
+    c2w[0, :3, :3] = np.eye(3, dtype=np.float32)
+    c2w[0, :3, 3] = 0.05
+    ref = R.flatten(R.llff_ndc_rays(c2w, h, w, focal, 0.0, 1.0))
+    rays = ops.generate_rays(torch.from_numpy(c2w).to(DEV), h, w, focal, 0.0, 1.0, ndc=True)
+    for k in rays._fields:
+        close(getattr(rays, k), torch.from_numpy(ref[k]), rtol=1e-5, atol=2e-6 * float(np.abs(ref[k]).max()), msg=k)

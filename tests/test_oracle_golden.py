@@ -159,3 +159,18 @@ def test_init_state_dict_matches_reference_layout(golden):
     ref = _sd(golden)
     for k in ref:
         torch.testing.assert_close(small[k], ref[k], rtol=0, atol=0)
+
+
+def test_raygen_oracle_equals_reference():
+    """oracle/raygen_oracle.py against the literal dataset.py / ray.py generators (tests/golden/raygen_golden.npz)."""
+    import os
+    import numpy as np
+    from oracle import raygen_oracle as R
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "raygen_golden.npz"))
+    for tag, fn in (("pinhole", R.pinhole_rays), ("pinhole_wide", R.pinhole_rays), ("llff_ndc", R.llff_ndc_rays)):
+        h, w, focal, near, far = z[tag + "/hwf"]
+        out = fn(z[tag + "/c2w"], int(h), int(w), float(focal), float(near), float(far))
+        for k, v in out.items():
+            assert np.array_equal(v, z[f"{tag}/{k}"]), (tag, k)
+    o, d = R.convert_to_ndc(z["ndc/origins"], z["ndc/directions"], 12.5, 20, 10)
+    assert np.array_equal(o, z["ndc/out_origins"]) and np.array_equal(d, z["ndc/out_directions"])
