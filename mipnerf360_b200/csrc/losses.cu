@@ -279,22 +279,33 @@ distortion_rg_kernel(const float* __restrict__ s_vals, const float* __restrict__
   if (!BWD) block_sum_to_partial<RG_THREADS>(block_acc, partials);
 }
 
-// per-ray proposal bounds, 8 lanes per ray: fine knots + fp64 prefix weights parked in shared memory, each lane
-// resolves E coarse intervals (strided, so the group writes 8 consecutive outputs)
+// per-ray proposal bounds, 8 lanes per ray: fine knots are read with coalesced cyclic loads straight into shared
+// memory (skewed layout: index + index/8, conflict-free for both cyclic and blocked access), fp64 prefix weights
+// beside them; each lane resolves E coarse intervals (strided, so the group writes 8 consecutive outputs).
+template <int E>
+__device__ __forceinline__ int rg_skew_l(int i) {
+  return i + (i >> (E == 4 ? 2 : E == 8 ? 3 : 4));
+}
+
 template <int E>
 __global__ void __launch_bounds__(RG_THREADS)
 bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
                  int B, float* __restrict__ b_out) {
-  constexpr int N = E * RG_LANES, K = N + 1;
-  __shared__ float s_tf[RG_RAYS_PER_BLOCK][K + 3];
-  __shared__ double s_cw[RG_RAYS_PER_BLOCK][K + 1];
+  constexpr int N = E * RG_LANES, K = N + 1, ROW = K + K / E + 2;
+  __shared__ float s_tf[RG_RAYS_PER_BLOCK][ROW];
+  __shared__ double s_cw[RG_RAYS_PER_BLOCK][ROW];
   const int gl = threadIdx.x & 7, g = threadIdx.x >> 3, j0 = gl * E;
+  float* tfs = s_tf[g];
+  double* cws = s_cw[g];
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
     const long long ray_raw = base + g;
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
-    float tf[E + 1], w[E];
-    rg_load_knots<E>(t_fine + ray * K, j0, tf);
+    const float* tfrow = t_fine + ray * K;
+#pragma unroll
+    for (int c = 0; c < E; ++c) tfs[rg_skew_l<E>(gl + RG_LANES * c)] = __ldg(tfrow + gl + RG_LANES * c);
+    if (gl == 0) tfs[rg_skew_l<E>(N)] = __ldg(tfrow + N);
+    float w[E];
     rg_load<E>(w_fine + ray * N + j0, w);
     double run = 0.0, ex[E];
 #pragma unroll
@@ -304,43 +315,58 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     }
     const double off = rg_scan_excl(run, gl);
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-      s_cw[g][j0 + i] = off + ex[i];
-      s_tf[g][j0 + i] = tf[i];
-    }
-    if (gl == RG_LANES - 1) {
-      s_cw[g][N] = off + run;
-      s_tf[g][N] = tf[E];
-    }
+    for (int i = 0; i < E; ++i) cws[rg_skew_l<E>(j0 + i)] = off + ex[i];
+    if (gl == RG_LANES - 1) cws[rg_skew_l<E>(N)] = off + run;
     __syncwarp();
-    const float* tc = t_coarse + ray * K;
-    // branch-free counting searches, the lane's E intervals in lock step:
+    // two-level counting search:
     //   first = #{j < N : t1_j = tf[j+1] < L}   (= first j with t1_j >= L),   nR = #{j < N : t0_j = tf[j] <= R}
+    // Level 1 (registers): end knots of the 8 lane chunks, t1 of the chunk's last interval (tf[(l+1)E]) for `first`,
+    // its t0 (tf[(l+1)E - 1]) for `nR`; whole chunks are a sum of predicates.  Level 2: log2(E) shared-memory
+    // probes inside the one partial chunk, the lane's E intervals in lock step.
+    float endF[RG_LANES], endR[RG_LANES];
+#pragma unroll
+    for (int l = 0; l < RG_LANES; ++l) {
+      endF[l] = tfs[rg_skew_l<E>((l + 1) * E)];
+      endR[l] = tfs[rg_skew_l<E>((l + 1) * E - 1)];
+    }
+    const float* tc = t_coarse + ray * K;
     float L[E], R[E];
-    int first[E], nR[E];
+    int first[E], nR[E], baseF[E], baseR[E];
 #pragma unroll
     for (int c = 0; c < E; ++c) {
       const int i = gl + RG_LANES * c;
       L[c] = __ldg(tc + i);
       R[c] = __ldg(tc + i + 1);
+      int nf = 0, nr = 0;
+#pragma unroll
+      for (int l = 0; l < RG_LANES; ++l) {
+        nf += (endF[l] < L[c]) ? 1 : 0;
+        nr += (endR[l] <= R[c]) ? 1 : 0;
+      }
+      // skewed positions of the partial chunks: knot E*n + o sits at (E+1)*n + o for o < E
+      baseF[c] = nf * (E + 1);
+      baseR[c] = nr * (E + 1);
       first[c] = 0;
       nR[c] = 0;
     }
 #pragma unroll
-    for (int step = N; step > 0; step >>= 1) {
+    for (int step = E / 2; step > 0; step >>= 1) {
 #pragma unroll
       for (int c = 0; c < E; ++c) {
-        const int pf = first[c] + step, pr = nR[c] + step;
-        const float vf = s_tf[g][min(pf, N)];      // tf[(pf-1)+1]
-        const float vr = s_tf[g][min(pr, N) - 1];  // tf[pr-1]
-        if (pf <= N && vf < L[c]) first[c] = pf;
-        if (pr <= N && vr <= R[c]) nR[c] = pr;
+        // (all-chunks-full cases probe past the row's knots into its padding / the next row: harmless, see below)
+        const float vf = tfs[min(baseF[c] + first[c] + step, ROW - 1)];      // t1 of interval E*nf + (first+step) - 1
+        const float vr = tfs[min(baseR[c] + nR[c] + step - 1, ROW - 1)];     // t0 of interval E*nr + (nR+step) - 1
+        if (vf < L[c]) first[c] += step;
+        if (vr <= R[c]) nR[c] += step;
       }
     }
 #pragma unroll
     for (int c = 0; c < E; ++c) {
+      // interval counts: f = E*nf + first, r = E*nr + nR; with every chunk full (nf or nr == 8) the count is N
+      const int nf = baseF[c] / (E + 1), nr = baseR[c] / (E + 1);
+      const int f = nf == RG_LANES ? N : nf * E + first[c], r = nr == RG_LANES ? N : nr * E + nR[c];
       float v = 0.f;
-      if (nR[c] - 1 >= first[c]) v = fmaxf((float)(s_cw[g][nR[c]] - s_cw[g][first[c]]), 0.f);
+      if (r - 1 >= f) v = fmaxf((float)(cws[rg_skew_l<E>(r)] - cws[rg_skew_l<E>(f)]), 0.f);
       if (active) b_out[ray * N + gl + RG_LANES * c] = v;
     }
     __syncwarp();

@@ -191,25 +191,38 @@ invert_kernel(const float* __restrict__ bins, const float* __restrict__ cdf, con
   }
 }
 
-// N in {32, 64, 128}: 8 lanes per ray (ray_group.cuh).  Weights and knots live in registers, the blur needs one
-// neighbour value from each adjacent lane, the CDF is a lane-local loop + 3-step group scan; CDF and bins are then
-// parked in shared memory for the binary searches, and the 8 lanes write 8 consecutive samples per step.
+// N in {32, 64, 128}: 8 lanes per ray (ray_group.cuh).  Weights live in registers (blocked: E contiguous per
+// lane), the blur needs one neighbour value from each adjacent lane, the CDF is a lane-local loop + 3-step group
+// scan.  Knots are read with coalesced cyclic loads straight into shared memory; CDF and bins sit there in a
+// skewed layout (index + index/8: blocked stores and cyclic stores are both bank-conflict free) for the searches,
+// and the 8 lanes write 8 consecutive samples per step.
+// skewed shared-memory index: one pad word per lane chunk of E knots (E = 4, 8, 16)
+template <int E>
+__device__ __forceinline__ int rg_skew(int i) {
+  return i + (i >> (E == 4 ? 2 : E == 8 ? 3 : 4));
+}
+
 template <int E>
 __global__ void __launch_bounds__(RG_THREADS)
 resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
                    const float* __restrict__ jitter, int B, float padding, int blur, float* __restrict__ new_t) {
-  constexpr int N = E * RG_LANES, K = N + 1;
-  __shared__ float s_cdf[RG_RAYS_PER_BLOCK][K + 3];
-  __shared__ float s_bins[RG_RAYS_PER_BLOCK][K + 3];
+  constexpr int N = E * RG_LANES, K = N + 1, ROW = K + K / E + 2;
+  __shared__ float s_cdf[RG_RAYS_PER_BLOCK][ROW];
+  __shared__ float s_bins[RG_RAYS_PER_BLOCK][ROW];
   const int gl = threadIdx.x & 7, g = threadIdx.x >> 3, j0 = gl * E;
   const float one_m_eps = 1.f - 1.1920928955078125e-07f;
+  float* cdf = s_cdf[g];
+  float* bins = s_bins[g];
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
     const long long ray_raw = base + g;
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
-    float w[E], t[E + 1];
+    float w[E];
     rg_load<E>(weights + ray * N + j0, w);
-    rg_load_knots<E>(t_vals + ray * K, j0, t);
+    const float* trow = t_vals + ray * K;
+#pragma unroll
+    for (int c = 0; c < E; ++c) bins[rg_skew<E>(gl + RG_LANES * c)] = __ldg(trow + gl + RG_LANES * c);
+    if (gl == 0) bins[rg_skew<E>(N)] = __ldg(trow + N);
     if (blur) {
       float wl = __shfl_up_sync(FULL_MASK, w[E - 1], 1, RG_LANES);
       float wr = __shfl_down_sync(FULL_MASK, w[0], 1, RG_LANES);
@@ -230,10 +243,13 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
     const float pad = fmaxf(0.f, 1e-5f - wsum);
     const float add = pad / (float)N;
     wsum = wsum + pad;
+    // pdf = (w + add) / wsum as a multiplication by the (correctly rounded) reciprocal: the CDF only has to agree
+    // with the reference to rounding (its scan order differs anyway); indices are exact GIVEN a CDF
+    const float inv_wsum = 1.f / wsum;
     float run = 0.f, incl[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      run += (w[i] + add) / wsum;
+      run += (w[i] + add) * inv_wsum;
       incl[i] = run;
     }
     const float off = rg_scan_excl(run, gl);
@@ -246,53 +262,60 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
     }
     pm = __shfl_up_sync(FULL_MASK, pm, 1, RG_LANES);
     if (gl == 0) pm = 0.f;
+    float my_last = 0.f;  // cdf[(gl+1)*E]: the last knot of this lane's chunk
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      s_cdf[g][j0 + i + 1] = (j0 + i == N - 1) ? 1.f : fminf(1.f, fmaxf(off + incl[i], pm));
-      s_bins[g][j0 + i] = t[i];
+      const float cv = (j0 + i == N - 1) ? 1.f : fminf(1.f, fmaxf(off + incl[i], pm));
+      cdf[rg_skew<E>(j0 + i + 1)] = cv;
+      my_last = cv;
     }
-    if (gl == 0) s_cdf[g][0] = 0.f;
-    if (gl == RG_LANES - 1) s_bins[g][N] = t[E];
-    __syncwarp();
-    // the lane's E searches advance in lock step (branch-free counting search): log2(N)+1 dependent shared-memory
-    // reads in total instead of per sample.  cnt = number of knots <= u, i.e. upper_bound.
-    float u[E];
-    int cnt[E];
+    if (gl == 0) cdf[0] = 0.f;
+    // two-level search, level 1 in registers: every lane of the group gets the 8 chunk-end knots
+    float chunk_end[RG_LANES];
 #pragma unroll
-    for (int c = 0; c < E; ++c) {
-      const int m = gl + RG_LANES * c;
+    for (int l = 0; l < RG_LANES; ++l) chunk_end[l] = __shfl_sync(FULL_MASK, my_last, l, RG_LANES);
+    __syncwarp();
+    // cnt = number of knots <= u (upper bound).  Level 1: whole chunks below u (sorted, so a sum of predicates);
+    // level 2: branch-free counting search inside the one partial chunk (at most E-1 of its knots are <= u), the
+    // lane's E (+1 for lane 0: sample N) searches advancing in lock step.
+    constexpr int S = E + 1;
+    float u[S];
+    int cbase[S], cnt[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      const int m = (c < E) ? gl + RG_LANES * c : N;
       u[c] = __ldg(u_base + m);
       if (jitter) {
         u[c] = (u[c] + u[c]) + __ldg(jitter + ray * K + m);  // the doubled stratum offset is the reference's (App. A5)
         u[c] = fminf(u[c], one_m_eps);
       }
-      cnt[c] = 0;
+      int nfull = 0;
+#pragma unroll
+      for (int l = 0; l < RG_LANES; ++l) nfull += (chunk_end[l] <= u[c]) ? 1 : 0;
+      // the partial chunk holds knots E*n+1 .. E*n+E, skewed position (E+1)*n + 1 + offset (contiguous up to E-1)
+      cbase[c] = min(nfull, RG_LANES - 1) * (E + 1);
+      cnt[c] = 0;  // nfull == 8 (u >= cdf[N] = 1) cannot happen: u <= 1 - eps
     }
 #pragma unroll
-    for (int step = N; step > 0; step >>= 1) {
+    for (int step = E / 2; step > 0; step >>= 1) {
 #pragma unroll
-      for (int c = 0; c < E; ++c) {
-        const int probe = cnt[c] + step;
-        const float v = s_cdf[g][min(probe, K) - 1];
-        if (probe <= K && v <= u[c]) cnt[c] = probe;
+      for (int c = 0; c < S; ++c) {
+        const float v = cdf[cbase[c] + cnt[c] + step];
+        if (v <= u[c]) cnt[c] += step;
       }
     }
 #pragma unroll
-    for (int c = 0; c < E; ++c) {
-      const int i0 = max(cnt[c] - 1, 0), i1 = min(cnt[c], N);
-      const float c0 = s_cdf[g][i0], c1 = s_cdf[g][i1];
-      const float b0 = s_bins[g][i0], b1 = s_bins[g][i1];
+    for (int c = 0; c < S; ++c) {
+      // knots <= u: knot 0, the full chunks and cnt of the partial chunk  =>  i0 = E*n + cnt, i1 = i0 + 1
+      const int p0 = cbase[c] + cnt[c], p1 = p0 + 1 + (cnt[c] == E - 1 ? 1 : 0);
+      const float c0 = cdf[p0], c1 = cdf[p1];
+      const float b0 = bins[p0], b1 = bins[p1];
       // clip(nan_to_num((u-c0)/(c1-c0), 0), 0, 1) without the special-value tests: a zero-width CDF step gives
       // +inf -> 1 when u > c0 and nan -> 0 when u == c0 (c0 <= u always holds for the selected knot)
       const float den = c1 - c0, num = u[c] - c0;
-      const float tt = den > 0.f ? fminf(fmaxf(num / den, 0.f), 1.f) : (num > 0.f ? 1.f : 0.f);
-      if (active) new_t[ray * K + gl + RG_LANES * c] = b0 + tt * (b1 - b0);
-    }
-    if (gl == 0) {  // sample N (the (N+1)-th): one per ray
-      float un = __ldg(u_base + N);
-      if (jitter) un = fminf((un + un) + __ldg(jitter + ray * K + N), one_m_eps);
-      const float x = invert_one(s_cdf[g], s_bins[g], N, un, nullptr);
-      if (active) new_t[ray * K + N] = x;
+      const float tt = den > 0.f ? fminf(fmaxf(__fdividef(num, den), 0.f), 1.f) : (num > 0.f ? 1.f : 0.f);
+      const int m = (c < E) ? gl + RG_LANES * c : N;
+      if (active && (c < E || gl == 0)) new_t[ray * K + m] = b0 + tt * (b1 - b0);
     }
     __syncwarp();
   }
