@@ -108,21 +108,25 @@ def run_cpu(sample_rays, steps, warmup):
 # clocks
 # -------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi sampled every 100 ms from before the warm-up; `window()` keeps the samples whose timestamp falls
+    inside the timed region (the recipe's clocks line of B200_PROFILING.md)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "200", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
+        import datetime
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.p is None:
             return out
+        time.sleep(0.25)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -130,23 +134,27 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, power, reasons = [], [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
+            if len(c) < 8:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1])); power.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(power), samples=len(sm),
-                       reasons=sorted(reasons))
+        inside = [r for r in rows if t_begin <= r[0] <= t_end] or rows[-3:]
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            reasons = set()
+            for r in inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in inside), power_w_max=max(r[3] for r in inside),
+                       samples=len(inside), reasons=sorted(reasons))
         return out
 
 
@@ -252,6 +260,12 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
         dist.init_process_group("nccl", device_id=dev)
     from mipnerf360_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):  # fresh checkout on a box with nvcc: build once (rank 0), never fall back
+        if rank == 0:
+            from mipnerf360_b200 import build
+            build.build()
+        if world > 1:
+            dist.barrier()
     from mipnerf360_b200.model import mipNeRF360
     from mipnerf360_b200.train import Trainer
 
@@ -266,10 +280,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         trainer.step(rays, pixels)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    t_begin = time.time()
     _lib.reset_launch_count()
     _lib.PROFILE = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -278,13 +293,14 @@ def main():
         trainer.step(rays, pixels)
     e1.record()
     barrier()
+    t_end = time.time()
     prof, _lib.PROFILE = _lib.PROFILE, None
     launches = _lib.launch_count()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_begin, t_end) if clocks else None
 
     # end to end through the public API: pinned host rays/pixels in, losses out, every step
     rays_h, pixels_h = synth_rays(args.rays, 1000 + rank, pin=True)

@@ -113,9 +113,16 @@ class _MLPFunction(torch.autograd.Function):
         grads_trunk = [None] * (2 * L)
         for l in range(L, 0, -1):  # trunk layer l maps saved[l-1] -> saved[l]
             lin = mlp.trunk[l - 1][0]
-            dW, db = ops.linear_wgrad(dz, saved[l - 1])
-            grads_trunk[2 * (l - 1)] = dW[: lin.out_features, : lin.in_features]
-            grads_trunk[2 * (l - 1) + 1] = db[: lin.out_features]
+            gw, gb = lin.weight.grad, lin.bias.grad
+            if (gw is not None and gb is not None and gw.is_contiguous() and gb.is_contiguous()
+                    and gw.dtype == torch.float32 and tuple(gw.shape) == (dz.shape[1], saved[l - 1].shape[1])):
+                # unpadded layer with preallocated .grad (e.g. the flat buffers of train.FlatAdamW): the split-K
+                # kernel accumulates straight into it; returning None tells autograd there is nothing left to add
+                ops.linear_wgrad(dz, saved[l - 1], dW=gw, db=gb)
+            else:
+                dW, db = ops.linear_wgrad(dz, saved[l - 1])
+                grads_trunk[2 * (l - 1)] = dW[: lin.out_features, : lin.in_features]
+                grads_trunk[2 * (l - 1) + 1] = db[: lin.out_features]
             if l > 1:
                 dz = ops.linear_dgrad(dz, layers[l - 1][1], saved[l - 1], acts[l - 2])
         return (None, None, *grads_trunk, *grads_head)

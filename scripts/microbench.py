@@ -88,6 +88,18 @@ def micro(out_path):
             dirs = torch.randn(B, 3, device=DEV)
             ms = timeit(lambda: ops.density_to_weight(t, w, dirs))
             rec("density_to_weight_fwd", ms, 4 * N + 4 * (N + 1) + 12 + 4 * N)
+            # K3 full compositing on the MLP head outputs (raw [B,N,4]) forward / backward
+            if B * N * 16 * 3 < 0.5 * free:
+                raw = torch.rand(B, N, 4, device=DEV)
+                ms = timeit(lambda: ops.composite_heads(raw, t, dirs, -1.0, 0.001, False))
+                rec("composite_fwd_heads", ms, 16 * N + 4 * (N + 1) + 12 + 20 + 4 * N)
+                g_rgb, g_w = torch.rand(B, 3, device=DEV), torch.rand(B, N, device=DEV)
+                g_raw = torch.empty_like(raw)
+                ms = timeit(lambda: ops.call("mip360_composite_bwd", raw.data_ptr(), None, t.data_ptr(), dirs.data_ptr(), B, N,
+                                             1, -1.0, 0.001, 0, g_rgb.data_ptr(), None, g_w.data_ptr(), None, None,
+                                             g_raw.data_ptr()))
+                rec("composite_bwd_heads", ms, 16 * N + 4 * (N + 1) + 12 + 12 + 4 * N + 16 * N)
+                del raw, g_rgb, g_w, g_raw
             t2 = (torch.rand(B, N + 1, device=DEV) * 0.3).cumsum_(-1).add_(0.1)
             ms = timeit(lambda: ops.bounds_per_ray(t, w, t2))
             rec("bounds_per_ray", ms, 4 * (3 * N + 2) + 4 * N)

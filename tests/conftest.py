@@ -16,6 +16,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """GPU box without the prebuilt library (e.g. a fresh checkout): build it once; nvcc is part of the image."""
+    lib = os.path.join(ROOT, "mipnerf360_b200", "lib", "libmip360_b200.so")
+    if torch.cuda.is_available() and not os.path.exists(lib):
+        from mipnerf360_b200 import build
+        build.build()
+
+
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
         return
