@@ -24,6 +24,7 @@ SIGNATURES = {
     "mip360_launch_count": [],
     "mip360_reset_launch_count": [],
     "mip360_sm_count": [],
+    "mip360_set_option": [c_int, c_int],
     "mip360_level0_t_vals": [P, P, P, P, P, c_int, c_int, P],
     "mip360_frustum_norm_sq": [P, P, c_int, P, c_int, c_int, P, P],
     "mip360_cast_ipe": [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P],
@@ -143,6 +144,15 @@ def launch_count():
 
 def reset_launch_count():
     load().mip360_reset_launch_count()
+
+
+OPT_RAY_GROUP, OPT_CTA_PAIR, OPT_SHORT_K = 0, 1, 2
+
+
+def set_option(key, value):
+    """Switch a kernel variant on/off (all variants compute the same function; see mip360_set_option)."""
+    if load().mip360_set_option(int(key), int(bool(value))) != 0:
+        raise Mip360Error(load().mip360_last_error().decode())
 
 
 def sm_count():

@@ -638,10 +638,10 @@ template <int EPI>
 static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
                            cudaStream_t stream) {
   // CTA pairs (cta_group::2) for the big layers; single CTAs when there are too few 256-row tiles to fill the pairs
-  static const bool pair_ok = getenv("MIP360_NO_CTA_PAIR") == nullptr;
+  const bool pair_ok = option(OPT_CTA_PAIR);
   if (p.N % 256 == 0 && p.K >= 512 && pair_ok && p.M >= 256 * (sm_count() / 2))
     return launch_linear<256, EPI, 2>(A, Bw, yprev, p, stream);
-  static const bool short_ok = getenv("MIP360_NO_SHORTK") == nullptr;
+  const bool short_ok = option(OPT_SHORT_K);
   if (p.N % 128 == 0 && p.K <= (EPI == EPI_DGRAD ? 256 : 128) && short_ok && p.M >= 128 * sm_count())
     return launch_linear<128, EPI, 1, 2>(A, Bw, yprev, p, stream);
   if (p.N % 256 == 0) return launch_linear<256, EPI, 1>(A, Bw, yprev, p, stream);
@@ -725,7 +725,7 @@ int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int
   MIP_REQUIRE(dY && X && dW, "linear_wgrad: null pointer");
   MIP_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0 && K % 64 == 0, "linear_wgrad: bad shape M=%d N=%d K=%d", M, N, K);
   WgradParams p{dW, db, M, N, K, 1};
-  static const bool pair_ok = getenv("MIP360_NO_CTA_PAIR") == nullptr;
+  const bool pair_ok = option(OPT_CTA_PAIR);
   if (K % 256 == 0 && N % 256 == 0 && N >= 512 && pair_ok) return launch_wgrad<256, 2>(dY, X, p, (cudaStream_t)stream);
   if (K % 256 == 0) return launch_wgrad<256, 1>(dY, X, p, (cudaStream_t)stream);
   if (K == 128) return launch_wgrad<128, 1>(dY, X, p, (cudaStream_t)stream);

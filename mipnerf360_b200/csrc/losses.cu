@@ -404,9 +404,9 @@ int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int 
   const int grid = B > 0 ? (rg ? rg_loss_grid(B) : ray_grid(B, LS_WARPS)) : 0;
   if (grid > 0) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 32) distortion_rg_kernel<4, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
-    else if (N == 64) distortion_rg_kernel<8, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
-    else if (N == 128) distortion_rg_kernel<16, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    if (rg && N == 32) distortion_rg_kernel<4, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    else if (rg && N == 64) distortion_rg_kernel<8, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
+    else if (rg && N == 128) distortion_rg_kernel<16, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
     else distortion_kernel<false><<<grid, LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, per_ray, partials, nullptr, nullptr);
     MIP_LAUNCH_CHECK();
   }
@@ -422,9 +422,10 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
   if (B <= 0) return MIP360_OK;
   {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 32) distortion_rg_kernel<4, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
-    else if (N == 64) distortion_rg_kernel<8, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
-    else if (N == 128) distortion_rg_kernel<16, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    const bool rg = rg_supported_host(N);
+    if (rg && N == 32) distortion_rg_kernel<4, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    else if (rg && N == 64) distortion_rg_kernel<8, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
+    else if (rg && N == 128) distortion_rg_kernel<16, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
     else distortion_kernel<true><<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
   }
   MIP_LAUNCH_CHECK();
@@ -438,9 +439,10 @@ int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float*
   if (B <= 0) return MIP360_OK;
   {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 32) bounds_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
-    else if (N == 64) bounds_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
-    else if (N == 128) bounds_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    const bool rg = rg_supported_host(N);
+    if (rg && N == 32) bounds_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    else if (rg && N == 64) bounds_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
+    else if (rg && N == 128) bounds_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
     else bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out);
   }
   MIP_LAUNCH_CHECK();

@@ -12,7 +12,7 @@ constexpr int RG_THREADS = 128;
 constexpr int RG_RAYS_PER_BLOCK = RG_THREADS / RG_LANES;
 
 __device__ __forceinline__ bool rg_supported(int N) { return N == 32 || N == 64 || N == 128; }
-static inline bool rg_supported_host(int N) { return N == 32 || N == 64 || N == 128; }
+static inline bool rg_supported_host(int N) { return (N == 32 || N == 64 || N == 128) && option(OPT_RAY_GROUP); }
 
 template <typename T>
 __device__ __forceinline__ T rg_sum(T v) {

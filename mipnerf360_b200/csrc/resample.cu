@@ -369,13 +369,14 @@ int mip360_resample(const float* t_vals, const float* weights, const float* u_ba
   MIP_REQUIRE(t_vals && weights && u_base && new_t, "resample: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  if (N == 32)
+  const bool rg = rg_supported_host(N);
+  if (rg && N == 32)
     resample_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
                                                                               resample_padding, blur, new_t);
-  else if (N == 64)
+  else if (rg && N == 64)
     resample_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
                                                                               resample_padding, blur, new_t);
-  else if (N == 128)
+  else if (rg && N == 128)
     resample_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
                                                                                resample_padding, blur, new_t);
   else

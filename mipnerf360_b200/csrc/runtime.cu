@@ -8,6 +8,9 @@ namespace mip360 {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_options[OPT_COUNT] = {{1}, {1}, {1}};
+
+bool option(int key) { return key >= 0 && key < OPT_COUNT && g_options[key].load(std::memory_order_relaxed) != 0; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -38,4 +41,12 @@ int mip360_version(void) { return 100; }
 long long mip360_launch_count(void) { return mip360::g_launches.load(); }
 void mip360_reset_launch_count(void) { mip360::g_launches.store(0); }
 int mip360_sm_count(void) { return mip360::sm_count(); }
+int mip360_set_option(int key, int value) {
+  if (key < 0 || key >= mip360::OPT_COUNT) {
+    mip360::set_error("set_option: unknown key %d", key);
+    return MIP360_ERR_ARG;
+  }
+  mip360::g_options[key].store(value != 0);
+  return MIP360_OK;
+}
 }

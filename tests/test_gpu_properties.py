@@ -153,3 +153,66 @@ def test_model_and_trainer_full_size():
     m2.load_state_dict(sd)
     for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_kernel_variants_agree(ops):
+    """The fast variants (8-lanes-per-ray register kernels, CTA-pair and short-K GEMM tiles) against the generic ones
+    on the same inputs, switched at run time through mip360_set_option."""
+    import math
+    from mipnerf360_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(11)
+    b = 4096
+    t = (torch.rand(b, N + 1, device=DEV, generator=g) * 0.3).cumsum(-1) + 0.1
+    t2 = (torch.rand(b, N + 1, device=DEV, generator=g) * 0.3).cumsum(-1) + 0.1
+    w = torch.rand(b, N, device=DEV, generator=g) * (2.0 / N)
+    raw = torch.rand(b, N, 4, device=DEV, generator=g)
+    dirs = torch.randn(b, 3, device=DEV, generator=g)
+    jit = ops.draw_jitter(b, N + 1, DEV)
+    gw, gc = torch.randn(b, N, device=DEV, generator=g), torch.randn(b, 3, device=DEV, generator=g)
+
+    def per_ray():
+        raw_d = raw.clone().requires_grad_(True)
+        c, d, a, ww = ops.composite_heads(raw_d, t, dirs, -1.0, 0.001, True)
+        ((ww * gw).sum() + (c * gc).sum()).backward()
+        w_d = w.clone().requires_grad_(True)
+        ld = ops.distortion_loss(t / t[:, -1:], w_d)
+        ld.backward()
+        return dict(resample=ops.resample(t, w, True, 0.01, jitter=jit), comp=c, dist=d, acc=a, weights=ww,
+                    g_raw=raw_d.grad, bounds=ops.bounds_per_ray(t, w, t2), loss_dist=ld, g_dist=w_d.grad)
+
+    fast = per_ray()
+    _lib.set_option(_lib.OPT_RAY_GROUP, False)
+    try:
+        slow = per_ray()
+    finally:
+        _lib.set_option(_lib.OPT_RAY_GROUP, True)
+    for k in fast:
+        scale = float(slow[k].abs().max()) + 1e-30
+        torch.testing.assert_close(fast[k], slow[k], rtol=2e-5, atol=2e-6 * scale, msg=lambda m, k=k: f"{k}: {m}")
+
+    # GEMM tile configurations: same K order per output element, so the results are bit-identical
+    M = 148 * 256 + 128
+    x = torch.randn(M, 1024, device=DEV, generator=g).to(torch.bfloat16)
+    W = (torch.randn(1024, 1024, device=DEV, generator=g) / 32).to(torch.bfloat16)
+    bias = torch.randn(1024, device=DEV, generator=g)
+    x0 = torch.randn(M, 64, device=DEV, generator=g).to(torch.bfloat16)
+    W0 = (torch.randn(1024, 64, device=DEV, generator=g) / 8).to(torch.bfloat16)
+    dY = torch.randn(M, 1024, device=DEV, generator=g).to(torch.bfloat16)
+
+    def gemms():
+        dW, db = ops.linear_wgrad(dY, x)
+        return dict(fwd=ops.linear_fwd(x, W, bias, 1)[0], dgrad=ops.linear_dgrad(dY, W.T.contiguous(), x, 1),
+                    fwd0=ops.linear_fwd(x0, W0, bias, 1)[0], dW=dW, db=db)
+
+    fast = gemms()
+    _lib.set_option(_lib.OPT_CTA_PAIR, False)
+    _lib.set_option(_lib.OPT_SHORT_K, False)
+    try:
+        slow = gemms()
+    finally:
+        _lib.set_option(_lib.OPT_CTA_PAIR, True)
+        _lib.set_option(_lib.OPT_SHORT_K, True)
+    for k in ("fwd", "dgrad", "fwd0"):
+        assert torch.equal(fast[k], slow[k]), k
+    for k in ("dW", "db"):  # split-K atomics: summation order differs
+        torch.testing.assert_close(fast[k], slow[k], rtol=1e-4, atol=1e-4 * math.sqrt(M))
