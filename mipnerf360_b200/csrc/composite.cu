@@ -481,8 +481,8 @@ extern "C" {
 int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
                          float* distance, float* acc, float* weights, mip360_stream_t stream) {
-  MIP_REQUIRE(rgb_or_raw && t_vals && dirs && comp_rgb && distance && acc, "composite_fwd: null pointer");
-  MIP_REQUIRE(head_mode == 1 || density, "composite_fwd: density missing");
+  MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs && comp_rgb && distance && acc), "composite_fwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_fwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
@@ -500,8 +500,8 @@ int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const fl
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in, float* g_density,
                          float* g_raw, mip360_stream_t stream) {
-  MIP_REQUIRE(rgb_or_raw && t_vals && dirs, "composite_bwd: null pointer");
-  MIP_REQUIRE(head_mode == 1 || density, "composite_bwd: density missing");
+  MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs), "composite_bwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_bwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
@@ -517,7 +517,7 @@ int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const fl
 
 int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, float* weights, mip360_stream_t stream) {
-  MIP_REQUIRE(density && t_vals && dirs && weights, "density_to_weight_fwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (density && t_vals && dirs && weights), "density_to_weight_fwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
@@ -534,7 +534,7 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
 int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, const float* g_w, float* g_density,
                                  mip360_stream_t stream) {
-  MIP_REQUIRE(density && t_vals && dirs && g_w && g_density, "density_to_weight_bwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (density && t_vals && dirs && g_w && g_density), "density_to_weight_bwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
@@ -551,7 +551,7 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
 
 int mip360_t_to_s(const float* t_vals, const float* near, const float* far, int B, int K, float* s_vals,
                   float* t_shift, mip360_stream_t stream) {
-  MIP_REQUIRE(t_vals && near && far && s_vals, "t_to_s: null pointer");
+  MIP_REQUIRE(B <= 0 || (t_vals && near && far && s_vals), "t_to_s: null pointer");
   if (B <= 0 || K <= 0) return MIP360_OK;
   const long long n = (long long)B * K;
   t_to_s_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t_vals, near, far, B, K, s_vals, t_shift);
@@ -561,7 +561,7 @@ int mip360_t_to_s(const float* t_vals, const float* near, const float* far, int 
 
 int mip360_s_to_t(const float* s_vals, const float* near, const float* far, int B, int K, float* t_vals,
                   mip360_stream_t stream) {
-  MIP_REQUIRE(s_vals && near && far && t_vals, "s_to_t: null pointer");
+  MIP_REQUIRE(B <= 0 || (s_vals && near && far && t_vals), "s_to_t: null pointer");
   if (B <= 0 || K <= 0) return MIP360_OK;
   const long long n = (long long)B * K;
   s_to_t_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s_vals, near, far, B, K, t_vals);

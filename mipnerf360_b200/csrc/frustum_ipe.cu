@@ -447,7 +447,7 @@ extern "C" {
 
 int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand, float* t_out,
                          int B, int N, mip360_stream_t stream) {
-  MIP_REQUIRE(near && far && s_lin && t_out, "level0_t_vals: null pointer");
+  MIP_REQUIRE(B <= 0 || (near && far && s_lin && t_out), "level0_t_vals: null pointer");
   MIP_REQUIRE(B >= 0 && N >= 1, "level0_t_vals: bad sizes B=%d N=%d", B, N);
   if (B == 0) return MIP360_OK;
   const long long total = (long long)B * (N + 1);
@@ -458,7 +458,7 @@ int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin
 
 int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const float* directions, int B, int N,
                            double* norm_sq, mip360_stream_t stream) {
-  MIP_REQUIRE(t0 && t1 && directions && norm_sq, "frustum_norm_sq: null pointer");
+  MIP_REQUIRE(B <= 0 || (t0 && t1 && directions && norm_sq), "frustum_norm_sq: null pointer");
   MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "frustum_norm_sq: bad sizes");
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
@@ -471,7 +471,7 @@ int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const
 int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
                     const float* vdir_enc, const float* radii, const double* norm_sq, int B, int N, int contract_mode,
                     int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16, mip360_stream_t stream) {
-  MIP_REQUIRE(t0 && t1 && directions && radii, "cast_ipe: null pointer");
+  MIP_REQUIRE(B <= 0 || (t0 && t1 && directions && radii), "cast_ipe: null pointer");
   MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "cast_ipe: bad sizes B=%d N=%d stride=%d", B, N, t_stride);
   MIP_REQUIRE(contract_mode >= 0 && contract_mode <= 2, "cast_ipe: contract_mode %d", contract_mode);
   MIP_REQUIRE(contract_mode != 0 || norm_sq, "cast_ipe: reference contraction needs norm_sq");
@@ -493,7 +493,7 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
 
 int mip360_gaussian_to_xyz(const float* directions, const float* t_mean, const float* t_var, const float* r_var, int B,
                            int N, float* means, float* covs, mip360_stream_t stream) {
-  MIP_REQUIRE(directions && t_mean && t_var && r_var && means && covs, "gaussian_to_xyz: null pointer");
+  MIP_REQUIRE(B <= 0 || (directions && t_mean && t_var && r_var && means && covs), "gaussian_to_xyz: null pointer");
   if (B <= 0) return MIP360_OK;
   const long long S = (long long)B * N;
   gaussian_to_xyz_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(directions, t_mean, t_var, r_var, S, N,
@@ -537,7 +537,7 @@ int mip360_ipe(const float* means, const float* covs, long long S, float* enc, m
 }
 
 int mip360_viewdir_enc(const float* viewdirs, int B, int min_deg, int max_deg, float* enc, mip360_stream_t stream) {
-  MIP_REQUIRE(viewdirs && enc, "viewdir_enc: null pointer");
+  MIP_REQUIRE(B <= 0 || (viewdirs && enc), "viewdir_enc: null pointer");
   MIP_REQUIRE(max_deg > min_deg, "viewdir_enc: empty scale range");
   if (B <= 0) return MIP360_OK;
   viewdir_enc_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(viewdirs, B, min_deg, max_deg, enc);

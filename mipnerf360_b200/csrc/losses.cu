@@ -397,7 +397,7 @@ int mip360_partials_len(int B) {
 
 int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int N, float* per_ray, double* partials,
                           float* loss, mip360_stream_t stream) {
-  MIP_REQUIRE(s_vals && weights && partials && loss, "distortion_fwd: null pointer");
+  MIP_REQUIRE(partials && loss && (B <= 0 || (s_vals && weights)), "distortion_fwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   MIP_REQUIRE(B >= 0, "distortion_fwd: B=%d", B);
   const bool rg = rg_supported_host(N);
@@ -417,7 +417,7 @@ int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int 
 
 int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int N, const float* g_loss_ptr, float* g_w,
                           mip360_stream_t stream) {
-  MIP_REQUIRE(s_vals && weights && g_loss_ptr && g_w, "distortion_bwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (s_vals && weights && g_loss_ptr && g_w), "distortion_bwd: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "distortion_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   {
@@ -434,7 +434,7 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
 
 int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N, float* b_out,
                           mip360_stream_t stream) {
-  MIP_REQUIRE(t_fine && w_fine && t_coarse && b_out, "bounds_per_ray: null pointer");
+  MIP_REQUIRE(B <= 0 || (t_fine && w_fine && t_coarse && b_out), "bounds_per_ray: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_per_ray: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   {
@@ -450,7 +450,7 @@ int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float*
 }
 
 int mip360_bounds_reduce(const float* b, int B, int N, double* bound_total, mip360_stream_t stream) {
-  MIP_REQUIRE(b && bound_total, "bounds_reduce: null pointer");
+  MIP_REQUIRE(B <= 0 || (b && bound_total), "bounds_reduce: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_reduce: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   const int target_blocks = sm_count() * 4;
@@ -464,8 +464,8 @@ int mip360_bounds_reduce(const float* b, int B, int N, double* bound_total, mip3
 
 int mip360_interlevel_fwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
                           int bound_mode, float batch_div, double* partials, float* loss, mip360_stream_t stream) {
-  MIP_REQUIRE(w_hat && partials && loss, "interlevel_fwd: null pointer");
-  MIP_REQUIRE(bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr, "interlevel_fwd: bound missing");
+  MIP_REQUIRE(partials && loss && (B <= 0 || w_hat), "interlevel_fwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr), "interlevel_fwd: bound missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "interlevel_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   const long long total = (long long)B * N;
   int grid = 0;
@@ -483,8 +483,8 @@ int mip360_interlevel_fwd(const float* w_hat, const float* b_per_ray, const doub
 int mip360_interlevel_bwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
                           int bound_mode, float batch_div, const float* g_loss_ptr, float* g_w_hat,
                           mip360_stream_t stream) {
-  MIP_REQUIRE(w_hat && g_loss_ptr && g_w_hat, "interlevel_bwd: null pointer");
-  MIP_REQUIRE(bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr, "interlevel_bwd: bound missing");
+  MIP_REQUIRE(B <= 0 || (w_hat && g_loss_ptr && g_w_hat), "interlevel_bwd: null pointer");
+  MIP_REQUIRE(B <= 0 || (bound_mode == 0 ? bound_total != nullptr : b_per_ray != nullptr), "interlevel_bwd: bound missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "interlevel_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   const long long total = (long long)B * N;
   if (total <= 0) return MIP360_OK;

@@ -335,7 +335,7 @@ extern "C" {
 
 int mip360_blur_weights(const float* weights, int B, int N, float resample_padding, float* out,
                         mip360_stream_t stream) {
-  MIP_REQUIRE(weights && out, "blur_weights: null pointer");
+  MIP_REQUIRE(B <= 0 || (weights && out), "blur_weights: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "blur_weights: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   blur_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, resample_padding, out);
@@ -344,7 +344,7 @@ int mip360_blur_weights(const float* weights, int B, int N, float resample_paddi
 }
 
 int mip360_resample_cdf(const float* weights, int B, int N, float* cdf, mip360_stream_t stream) {
-  MIP_REQUIRE(weights && cdf, "resample_cdf: null pointer");
+  MIP_REQUIRE(B <= 0 || (weights && cdf), "resample_cdf: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample_cdf: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   cdf_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, cdf);
@@ -354,7 +354,7 @@ int mip360_resample_cdf(const float* weights, int B, int N, float* cdf, mip360_s
 
 int mip360_resample_invert(const float* bins, const float* cdf, const float* u, int u_row_stride, int B, int N, int M,
                            float* samples, int32_t* idx, mip360_stream_t stream) {
-  MIP_REQUIRE(bins && cdf && u && samples, "resample_invert: null pointer");
+  MIP_REQUIRE(B <= 0 || (bins && cdf && u && samples), "resample_invert: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample_invert: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   MIP_REQUIRE(M >= 1, "resample_invert: M=%d", M);
   if (B <= 0) return MIP360_OK;
@@ -366,7 +366,7 @@ int mip360_resample_invert(const float* bins, const float* cdf, const float* u, 
 
 int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter, int B, int N,
                     float resample_padding, int blur, float* new_t, mip360_stream_t stream) {
-  MIP_REQUIRE(t_vals && weights && u_base && new_t, "resample: null pointer");
+  MIP_REQUIRE(B <= 0 || (t_vals && weights && u_base && new_t), "resample: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   const bool rg = rg_supported_host(N);

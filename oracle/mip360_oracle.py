@@ -157,7 +157,7 @@ def level0_t_vals(near, far, num_samples, randomized, t_rand=None):
         upper = torch.cat([mids, t[..., -1:]], -1)
         lower = torch.cat([t[..., :1], mids], -1)
         if t_rand is None:
-            t_rand = torch.rand(near.shape[0], num_samples + 1, dtype=near.dtype)
+            t_rand = torch.rand(near.shape[0], num_samples + 1, dtype=near.dtype, device=near.device)
         t = lower + (upper - lower) * t_rand
     else:
         t = t.expand(near.shape[0], num_samples + 1).clone()
@@ -190,18 +190,19 @@ def pdf_to_cdf(weights):
     return torch.cat([zeros, cdf, zeros + 1], dim=-1)
 
 
-def pdf_uniforms(batch, num_samples, randomized, dtype=torch.float32, jitter=None):
+def pdf_uniforms(batch, num_samples, randomized, dtype=torch.float32, jitter=None, device=None):
     """intern/ray.py:29-39.  ``jitter`` = the uniform_(0, 1/M - eps) draw of ray.py:33.
     The stratum offset is doubled in the source (App. A5) and reproduced here."""
     eps32 = torch.finfo(torch.float32).eps
+    device = jitter.device if jitter is not None else (device or "cpu")
     if randomized:
         s = 1 / num_samples
-        u = (torch.arange(num_samples) * s).to(dtype)[None, :]
+        u = (torch.arange(num_samples, device=device) * s).to(dtype)[None, :]
         if jitter is None:
-            jitter = torch.empty(batch, num_samples, dtype=dtype).uniform_(to=(s - eps32))
+            jitter = torch.empty(batch, num_samples, dtype=dtype, device=device).uniform_(to=(s - eps32))
         u = u + u + jitter
         return torch.minimum(u, torch.full_like(u, 1.0 - eps32))
-    u = torch.linspace(0.0, 1.0 - eps32, num_samples, dtype=dtype)
+    u = torch.linspace(0.0, 1.0 - eps32, num_samples, dtype=dtype, device=device)
     return u.expand(batch, num_samples)
 
 
@@ -222,7 +223,7 @@ def invert_cdf(bins, cdf, u):
 def sorted_piecewise_constant_pdf(bins, weights, num_samples, randomized=True, jitter=None, return_aux=False):
     """intern/ray.py:12-57."""
     cdf = pdf_to_cdf(weights)
-    u = pdf_uniforms(weights.shape[0], num_samples, randomized, weights.dtype, jitter)
+    u = pdf_uniforms(weights.shape[0], num_samples, randomized, weights.dtype, jitter, device=weights.device)
     samples, i0 = invert_cdf(bins, cdf, u)
     if return_aux:
         return samples, cdf, u, i0

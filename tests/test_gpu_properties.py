@@ -216,3 +216,89 @@ def test_kernel_variants_agree(ops):
         assert torch.equal(fast[k], slow[k]), k
     for k in ("dW", "db"):  # split-K atomics: summation order differs
         torch.testing.assert_close(fast[k], slow[k], rtol=1e-4, atol=1e-4 * math.sqrt(M))
+
+
+def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu():
+    """BASELINE size (16 384 rays x 64 samples, default widths): the bf16 tcgen05 path against the fp32 oracle
+    evaluated ON THE GPU (plain torch fp32 ops, TF32 off) with the same weights and the same random draws.
+    Stated bf16 tolerances: per-ray outputs |err| <= 2e-2, mean |err| <= 2e-3; losses 2 %; per-tensor gradient
+    relative Frobenius error <= 6 %."""
+    from mipnerf360_b200 import mlp as MLP
+    from mipnerf360_b200 import ops
+    from mipnerf360_b200.intern.loss import Loss_dist, Loss_nerf, Loss_prop
+    from mipnerf360_b200.model import mipNeRF360
+    from oracle import mip360_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rays = _rays(B, 21)
+    g = torch.Generator(device=DEV).manual_seed(22)
+    t_rand = torch.rand(B, N + 1, device=DEV, generator=g)
+    jitter = torch.empty(B, N + 1, device=DEV).uniform_(0, 1 / (N + 1) - torch.finfo(torch.float32).eps, generator=g)
+    pixels = torch.rand(B, 3, device=DEV, generator=g)
+    sd = {k: v.to(DEV) for k, v in O.init_state_dict(seed=0).items()}
+    m = mipNeRF360(randomized=True, num_samples=N, device=torch.device(DEV))
+    m.load_state_dict(sd)
+
+    # fp32 oracle on the device
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    orays = O.Rays(*rays)
+    t_hat_r, w_hat_r = O.prop_forward(params, orays, N, True, t_rand=t_rand)
+    rgb_r, dist_r, acc_r, t_r, w_r, s_r = O.nerf_forward(params, orays, t_hat_r.detach(), w_hat_r.detach(), True, jitter=jitter)
+    lp_r = O.Loss_prop(t_r.detach(), w_r.detach(), t_hat_r, w_hat_r)
+    ln_r, _ = O.Loss_nerf(rgb_r, pixels)
+    ld_r = O.loss_dist(s_r, w_r)
+    names_p = [k for k in params if k.startswith("prop_net")]
+    names_n = [k for k in params if k.startswith("nerf_net")]
+    gp_r = torch.autograd.grad(lp_r, [params[k] for k in names_p])
+    gn_r = torch.autograd.grad(ln_r + 0.01 * ld_r, [params[k] for k in names_n])
+    gp_r, gn_r = [x.detach() for x in gp_r], [x.detach() for x in gn_r]
+    ref = [x.detach() for x in (t_hat_r, w_hat_r, rgb_r, acc_r, w_r, s_r, lp_r, ln_r, ld_r, t_r)]
+    del params, rgb_r, w_r, lp_r, ln_r, ld_r
+    torch.cuda.empty_cache()
+    t_hat_r, w_hat_r, rgb_r, acc_r, w_r, s_r, lp_r, ln_r, ld_r, t_r = ref
+
+    # the product path with the same draws
+    vd = m.prop_net.viewdirs_encoding(rays.viewdirs)
+    t_hat = ops.level0_t_vals(rays.near, rays.far, N, True, t_rand)
+    assert torch.equal(t_hat, t_hat_r)
+    x = ops.cast_ipe(t_hat, rays.origins, rays.directions, rays.radii, vd, want_x=True)["x"]
+    w_hat = ops.density_to_weight(t_hat, MLP.mlp_apply(m.prop_net._packed, x).view(B, N), rays.directions,
+                                  raw_logits=True, density_bias=-1)
+    new_t = ops.resample(t_hat_r, w_hat_r, True, 0.01, jitter=jitter)
+    # (own CDF vs torch.cumsum differ by rounding; a uniform within that rounding of a knot moves its sample a little)
+    torch.testing.assert_close(new_t + 1e-6, t_r, rtol=1e-4, atol=1e-4)
+    x = ops.cast_ipe(new_t, rays.origins, rays.directions, rays.radii, vd, want_x=True)["x"]
+    raw = MLP.mlp_apply(m.nerf_net._packed, x)
+    rgb, dist, acc, w = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions, -1, 0.001, False)
+    s, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
+    for name, a, b in (("w_hat", w_hat, w_hat_r), ("rgb", rgb, rgb_r), ("acc", acc, acc_r), ("w", w, w_r)):
+        err = (a.detach() - b).abs()
+        assert float(err.max()) <= 2e-2 and float(err.mean()) <= 2e-3, (name, float(err.max()), float(err.mean()))
+    lp = Loss_prop(t_shift, w.detach(), t_hat, w_hat)
+    ln, _ = Loss_nerf(rgb, pixels)
+    ld = Loss_dist(s, w)
+    for name, a, b in (("loss_prop", lp, lp_r), ("loss_nerf", ln, ln_r), ("loss_dist", ld, ld_r)):
+        assert abs(float(a) - float(b)) <= 2e-2 * abs(float(b)) + 1e-4, (name, float(a), float(b))
+    gp = torch.autograd.grad(lp, list(m.prop_net.parameters()))
+    gn = torch.autograd.grad(ln + 0.01 * ld, list(m.nerf_net.parameters()))
+    worst = 0.0
+    for k, a, b in list(zip(names_p, gp, gp_r)) + list(zip(names_n, gn, gn_r)):
+        rel = float((a - b).norm() / (b.norm() + 1e-20))
+        worst = max(worst, rel)
+        assert rel <= 6e-2, (k, rel)
+    print("full-size worst relative gradient error:", worst)
+
+
+def test_empty_batches_and_size_limits(ops):
+    from mipnerf360_b200 import _lib
+    e = lambda *s: torch.empty(*s, device=DEV)
+    assert ops.resample(e(0, N + 1), e(0, N), True, 0.01).shape == (0, N + 1)
+    assert ops.density_to_weight(e(0, N + 1), e(0, N), e(0, 3)).shape == (0, N)
+    c, d, a, w = ops.composite(e(0, N, 3), e(0, N, 1), e(0, N + 1), e(0, 3), False)
+    assert c.shape == (0, 3) and w.shape == (0, N)
+    assert float(ops.distortion_loss(e(0, N + 1), e(0, N))) == 0.0
+    assert ops.bounds_per_ray(e(0, N + 1), e(0, N), e(0, N + 1)).shape == (0, N)
+    assert ops.viewdir_enc(e(0, 3)).shape == (0, 16)
+    with pytest.raises(_lib.Mip360Error):  # more samples per ray than one warp holds
+        ops.resample(e(2, 131), e(2, 130), False, 0.01)
+    with pytest.raises(_lib.Mip360Error):
+        ops.composite(e(2, 200, 3), e(2, 200, 1), e(2, 201), e(2, 3), False)
