@@ -206,6 +206,25 @@ int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int
                         mip360_stream_t stream);
 int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_t* Wb, uint16_t* Wt,
                        mip360_stream_t stream);
+/* One layer of an MLP as the GEMM kernels consume it (all device pointers, widths zero padded to 64/128/256k). */
+typedef struct mip360_layer {
+  const uint16_t* W;  /* bf16 [n_pad, k_pad] */
+  const uint16_t* Wt; /* bf16 [k_pad, n_pad] = W^T, needed by the backward pass (NULL for inference) */
+  const float* bias;  /* fp32 [n_pad] */
+  int n_pad, k_pad;
+  int act;            /* activation applied to this layer's output: 0 none, 1 ReLU, 2 Sigmoid */
+} mip360_layer;
+/* Whole-MLP forward (model.py:91 / :179-181): x bf16 [M, trunk[0].k_pad] -> head outputs out fp32 [M, n_valid].
+ *   head: the (merged) output layer, n_pad = 64.  acts: n_act_bufs = n_trunk buffers [M, n_pad_l] to keep every
+ *   trunk activation for the backward pass, or 2 ping-pong buffers [M, max n_pad] for inference.
+ * Whole-MLP backward: g_out = dL/d out [M, n_valid], out = the saved head outputs (needed when head->act == 2).
+ *   dW[l] fp32 [n_pad_l, k_pad_l] and db[l] [n_pad_l] for l < n_trunk, dW[n_trunk] [64, k_pad] / db[n_trunk] [64]
+ *   for the head, all ACCUMULATED into (split-K atomics).  dz_head [M,64], dz0, dz1 [M, max n_pad]: bf16 scratch. */
+int mip360_mlp_fwd(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const mip360_layer* head,
+                   int n_valid, uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream);
+int mip360_mlp_bwd(const float* g_out, const float* out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
+                   const mip360_layer* head, int n_valid, uint16_t* const* acts, float* const* dW, float* const* db,
+                   uint16_t* dz_head, uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream);
 /* number of SMs the persistent GEMM grids are sized for (148 on B200) */
 int mip360_sm_count(void);
 

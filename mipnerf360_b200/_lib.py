@@ -56,6 +56,8 @@ SIGNATURES = {
     "mip360_linear_dgrad": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "mip360_linear_wgrad": [P, P, c_int, c_int, c_int, P, P, P],
     "mip360_cast_weight": [P, c_int, c_int, c_int, c_int, P, P, P],
+    "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
+    "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
     "mip360_adamw": [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P],
 }
@@ -64,6 +66,13 @@ _RESTYPES = {
     "mip360_launch_count": c_longlong,
     "mip360_reset_launch_count": None,
 }
+
+
+
+class Layer(ctypes.Structure):
+    """struct mip360_layer of include/mip360_b200.h."""
+    _fields_ = [("W", c_void_p), ("Wt", c_void_p), ("bias", c_void_p), ("n_pad", c_int), ("k_pad", c_int), ("act", c_int)]
+
 
 _lib = None
 

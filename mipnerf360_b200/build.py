@@ -25,6 +25,7 @@ SOURCES = {
     "losses.cu": ["--fmad=false"],
     "raygen.cu": ["--fmad=false"],
     "gemm_tcgen05.cu": [],
+    "mlp_api.cu": [],
 }
 
 

@@ -8,7 +8,9 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+import ctypes
+
+from . import _lib, ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID
 
 
@@ -68,7 +70,18 @@ class PackedMLP:
             bias[: bh.numel()] = bh
             self._packed = (layers, (Wb, Wt, bias))
             self._key = key
+            # the same tables as `struct mip360_layer` arrays for the one-call C entry points
+            acts = [a for _, a in self.trunk]
+            arr = (_lib.Layer * len(layers))()
+            for i, ((W_, Wt_, b_), a) in enumerate(zip(layers, acts)):
+                arr[i] = _lib.Layer(W_.data_ptr(), Wt_.data_ptr(), b_.data_ptr(), W_.shape[0], W_.shape[1], a)
+            head = _lib.Layer(Wb.data_ptr(), Wt.data_ptr(), bias.data_ptr(), 64, Wb.shape[1], self.head_act)
+            self._cstructs = (arr, head)
         return self._packed
+
+    def cstructs(self):
+        self.packed()
+        return self._cstructs
 
 
 class _MLPFunction(torch.autograd.Function):
@@ -80,13 +93,29 @@ class _MLPFunction(torch.autograd.Function):
         layers, (Wh, Wht, bh) = mlp.packed()
         need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside forward(); autograd tells us here
         acts = [a for _, a in mlp.trunk]
-        saved = [x]
-        h = x
-        for (Wb, _, bias), act in zip(layers, acts):
-            h, _ = ops.linear_fwd(h, Wb, bias, act)
+        M, L = x.shape[0], len(layers)
+        if _lib.PROFILE is not None:
+            # instrumented runs (bench.py's per-kernel table): one C call per GEMM so that each launch is timed
+            saved = [x]
+            h = x
+            for (Wb, _, bias), act in zip(layers, acts):
+                h, _ = ops.linear_fwd(h, Wb, bias, act)
+                if need_grad:
+                    saved.append(h)
+            _, out = ops.linear_fwd(h, Wh, bh, mlp.head_act, out_f32_cols=mlp.n_valid, want_bf16=False)
+        else:
+            # product path: the whole MLP is one call into the C ABI (mip360_mlp_fwd)
+            trunk_arr, head = mlp.cstructs()
             if need_grad:
-                saved.append(h)
-        _, out = ops.linear_fwd(h, Wh, bh, mlp.head_act, out_f32_cols=mlp.n_valid, want_bf16=False)
+                bufs = [torch.empty((M, Wb.shape[0]), device=x.device, dtype=torch.bfloat16) for Wb, _, _ in layers]
+            else:
+                wmax = max(Wb.shape[0] for Wb, _, _ in layers)
+                bufs = [torch.empty((M, wmax), device=x.device, dtype=torch.bfloat16) for _ in range(2)]
+            out = torch.empty((M, mlp.n_valid), device=x.device, dtype=torch.float32)
+            ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+            _lib.call("mip360_mlp_fwd", x.data_ptr(), M, trunk_arr, L, ctypes.byref(head), mlp.n_valid, ptrs, len(bufs),
+                      out.data_ptr())
+            saved = [x] + bufs
         if need_grad:
             ctx.mlp = mlp
             ctx.acts = acts
@@ -99,32 +128,53 @@ class _MLPFunction(torch.autograd.Function):
         out, *saved = ctx.saved_tensors  # saved[0] = x, saved[l] = output of trunk layer l
         layers, (Wh, Wht, bh) = mlp.packed()
         L = len(layers)
-        # head: dZ_head (bf16, padded to 64 columns) with the head activation derivative folded in
-        dzh = ops.head_grad_pack(g_out, out if mlp.head_act == ACT_SIGMOID else None, mlp.head_act)
-        dWh, dbh = ops.linear_wgrad(dzh, saved[L])
+        M = saved[0].shape[0]
+        dev = saved[0].device
+
+        def grad_targets(lin, n_pad, k_pad):
+            """(dW, db, direct): the layer's preallocated .grad buffers when they can be accumulated into directly
+            (unpadded layer, e.g. views of train.FlatAdamW's flat buffer), else fresh zero-initialised scratch."""
+            gw, gb = lin.weight.grad, lin.bias.grad
+            if (gw is not None and gb is not None and gw.is_contiguous() and gb.is_contiguous()
+                    and gw.dtype == torch.float32 and tuple(gw.shape) == (n_pad, k_pad)):
+                return gw, gb, True
+            return (torch.zeros((n_pad, k_pad), device=dev, dtype=torch.float32),
+                    torch.zeros((n_pad,), device=dev, dtype=torch.float32), False)
+
+        targets = [grad_targets(mlp.trunk[l][0], layers[l][0].shape[0], layers[l][0].shape[1]) for l in range(L)]
+        dWh = torch.zeros((64, Wh.shape[1]), device=dev, dtype=torch.float32)
+        dbh = torch.zeros((64,), device=dev, dtype=torch.float32)
+        if _lib.PROFILE is not None:
+            dzh = ops.head_grad_pack(g_out, out if mlp.head_act == ACT_SIGMOID else None, mlp.head_act)
+            ops.linear_wgrad(dzh, saved[L], dW=dWh, db=dbh)
+            dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
+            for l in range(L, 0, -1):  # trunk layer l maps saved[l-1] -> saved[l]
+                ops.linear_wgrad(dz, saved[l - 1], dW=targets[l - 1][0], db=targets[l - 1][1])
+                if l > 1:
+                    dz = ops.linear_dgrad(dz, layers[l - 1][1], saved[l - 1], acts[l - 2])
+        else:
+            trunk_arr, head = mlp.cstructs()
+            wmax = max(Wb.shape[0] for Wb, _, _ in layers)
+            dzh = torch.empty((M, 64), device=dev, dtype=torch.bfloat16)
+            dz0 = torch.empty((M, wmax), device=dev, dtype=torch.bfloat16)
+            dz1 = torch.empty((M, wmax), device=dev, dtype=torch.bfloat16)
+            act_ptrs = (ctypes.c_void_p * L)(*[a.data_ptr() for a in saved[1:]])
+            dW_ptrs = (ctypes.c_void_p * (L + 1))(*([t[0].data_ptr() for t in targets] + [dWh.data_ptr()]))
+            db_ptrs = (ctypes.c_void_p * (L + 1))(*([t[1].data_ptr() for t in targets] + [dbh.data_ptr()]))
+            g = ops.f32c(g_out)
+            _lib.call("mip360_mlp_bwd", g.data_ptr(), out.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
+                      ctypes.byref(head), mlp.n_valid, act_ptrs, dW_ptrs, db_ptrs, dzh.data_ptr(), dz0.data_ptr(),
+                      dz1.data_ptr())
+        grads_trunk = []
+        for (dW, db, direct), (lin, _) in zip(targets, mlp.trunk):
+            # direct: already accumulated into .grad; returning None tells autograd there is nothing left to add
+            grads_trunk += [None, None] if direct else [dW[: lin.out_features, : lin.in_features], db[: lin.out_features]]
         grads_head = []
         r = 0
         for h in mlp.heads:
             n = h.out_features
             grads_head += [dWh[r:r + n, : h.in_features], dbh[r:r + n]]
             r += n
-        # into the trunk: derivative of the last trunk activation from its saved output
-        dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
-        grads_trunk = [None] * (2 * L)
-        for l in range(L, 0, -1):  # trunk layer l maps saved[l-1] -> saved[l]
-            lin = mlp.trunk[l - 1][0]
-            gw, gb = lin.weight.grad, lin.bias.grad
-            if (gw is not None and gb is not None and gw.is_contiguous() and gb.is_contiguous()
-                    and gw.dtype == torch.float32 and tuple(gw.shape) == (dz.shape[1], saved[l - 1].shape[1])):
-                # unpadded layer with preallocated .grad (e.g. the flat buffers of train.FlatAdamW): the split-K
-                # kernel accumulates straight into it; returning None tells autograd there is nothing left to add
-                ops.linear_wgrad(dz, saved[l - 1], dW=gw, db=gb)
-            else:
-                dW, db = ops.linear_wgrad(dz, saved[l - 1])
-                grads_trunk[2 * (l - 1)] = dW[: lin.out_features, : lin.in_features]
-                grads_trunk[2 * (l - 1) + 1] = db[: lin.out_features]
-            if l > 1:
-                dz = ops.linear_dgrad(dz, layers[l - 1][1], saved[l - 1], acts[l - 2])
         return (None, None, *grads_trunk, *grads_head)
 
 
