@@ -240,6 +240,10 @@ int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W
                          int ndc, float ndc_near, float* origins, float* directions, float* viewdirs, float* radii,
                          float* near_out, float* far_out, mip360_stream_t stream);
 
+/* intern/utils.py:17-21 (to8b, used by model.render_image, model.py:270): uint8 = 255 * clip(nan_to_num(x), 0, 1),
+ * truncated like NumPy's astype(uint8); n elements (the image leaves the device as 3 B/pixel). */
+int mip360_to8b(const float* x, long long n, uint8_t* out, mip360_stream_t stream);
+
 /* fused AdamW over one flat fp32 parameter tensor (train.py:38,63,81 — "next" row f3 of SURVEY §8):
  * decoupled weight decay, bias correction from `step` (1-based), optional bf16 re-cast of the weights */
 int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

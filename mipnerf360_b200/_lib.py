@@ -59,6 +59,7 @@ SIGNATURES = {
     "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
+    "mip360_to8b": [P, c_longlong, P, P],
     "mip360_adamw": [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P],
 }
 _RESTYPES = {

@@ -101,9 +101,25 @@ raygen_kernel(const RayGenParams p, float* __restrict__ origins, float* __restri
   far_out[e] = p.far;
 }
 
+// intern/utils.py:17-21 (to8b): (255 * clip(nan_to_num(x), 0, 1)).astype(uint8) — truncation, as NumPy's cast
+__global__ void __launch_bounds__(256) to8b_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(nan_to_num_f(x[i]), 0.f), 1.f);
+  out[i] = (uint8_t)(255.f * v);
+}
+
 }  // namespace mip360
 
 using namespace mip360;
+
+extern "C" int mip360_to8b(const float* x, long long n, uint8_t* out, mip360_stream_t stream) {
+  MIP_REQUIRE(n <= 0 || (x && out), "to8b: null pointer");
+  if (n <= 0) return MIP360_OK;
+  to8b_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
 
 extern "C" int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal, float near,
                                     float far, int ndc, float ndc_near, float* origins, float* directions,

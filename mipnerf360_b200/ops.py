@@ -498,3 +498,12 @@ def generate_rays(cam_to_world, h, w, focal, near, far, ndc=False, ndc_near=1.0)
     call("mip360_generate_rays", ptr(c2w), c2w.shape[1], c2w.shape[0], int(h), int(w), float(focal), float(near),
          float(far), int(bool(ndc)), float(ndc_near), ptr(o), ptr(d), ptr(v), ptr(r), ptr(nr), ptr(fr))
     return Rays(o, d, v, r, nr, fr)
+
+
+def to8b(img):
+    """intern/utils.py:17-21 on the device: float image -> uint8 (255 * clip(nan_to_num(x), 0, 1), truncated)."""
+    x = f32c(img)
+    check_cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    call("mip360_to8b", ptr(x), x.numel(), ptr(out))
+    return out

@@ -600,3 +600,11 @@ def test_ray_generation_vs_reference_and_oracle(ops):
     rays = ops.generate_rays(torch.from_numpy(c2w).to(DEV), h, w, focal, 0.0, 1.0, ndc=True)
     for k in rays._fields:
         close(getattr(rays, k), torch.from_numpy(ref[k]), rtol=1e-5, atol=2e-6 * float(np.abs(ref[k]).max()), msg=k)
+
+
+def test_to8b_matches_numpy(ops):
+    import numpy as np
+    from mipnerf360_b200.intern.utils import to8b as to8b_host
+    x = torch.randn(37, 53, 3, device=DEV) * 0.7 + 0.5
+    x[0, 0, 0], x[0, 0, 1], x[0, 0, 2] = float("nan"), float("inf"), -float("inf")
+    assert np.array_equal(ops.to8b(x).cpu().numpy(), to8b_host(x.cpu().numpy()))
