@@ -244,6 +244,37 @@ int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W
  * truncated like NumPy's astype(uint8); n elements (the image leaves the device as 3 B/pixel). */
 int mip360_to8b(const float* x, long long n, uint8_t* out, mip360_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Depth / normal visualisation of a rendered frame    intern/pose.py:112-212
+ *   mip360_normals_scaling: pose.py:130-136 — over the non-NaN pixels of depth [H,W]: stats[0] count,
+ *       [1..3] mean of (x = column, y = row, depth), [4..6] their population variances,
+ *       [7] scaling = sqrt(((var x + var y)/2) / var depth).  fp64, two passes, deterministic.
+ *       partials: mip360_vis_partials_len() doubles of workspace.
+ *   mip360_visualize_normals: pose.py:112-121 + :137-145 — normals of stats[7] * depth through the 3x3
+ *       blur/edge convolutions (zero fill outside the frame, as scipy 'same'), shaded (n + 1)/2 with
+ *       NaN -> 1, blended to white by acc (optional).  Writes vis [H,W,3] fp32 and/or vis8 [H,W,3] uint8
+ *       (= to8b(vis), utils.py:17-21).
+ *   mip360_depth_range: pose.py:180-194 — range[0] = near, range[1] = far; a value whose auto_* flag is set
+ *       is replaced by the acc-weighted quantile of depth the reference reads off its argsort + cumsum:
+ *       near = first depth (ascending, NaN last) whose cumulative acc >= ignore_frac * total, minus eps;
+ *       far = last depth whose cumulative acc <= (1 - ignore_frac) * total, plus eps.  Found without a sort
+ *       by a 32-step bisection over the order-preserving integer image of the depths; acc enters in exact
+ *       integer units of 2^-24.  work: mip360_vis_work_len() unsigned 64-bit words.
+ *   mip360_visualize_depth: pose.py:196-212 — curve (0: -log(x+eps), 1: x, 2: 1/(x+eps), 3: log(x+eps)) applied
+ *       to depth, near, far; modulus > 0: value = mod(curved, modulus)/modulus, else clip((curved - min)/|far - near|);
+ *       colour = lut[trunc(value * n_lut)] (lut [n_lut,3] fp32, listed-colour-map indexing) or, with lut NULL,
+ *       the sinebow map (pose.py:123-126); blended to white by acc (NaN depth -> acc 0).
+ * ------------------------------------------------------------------------------------------ */
+int mip360_vis_partials_len(void);
+int mip360_vis_work_len(void);
+int mip360_normals_scaling(const float* depth, int H, int W, double* partials, double* stats, mip360_stream_t stream);
+int mip360_visualize_normals(const float* depth, const float* acc, const double* stats, int H, int W, float* vis,
+                             uint8_t* vis8, mip360_stream_t stream);
+int mip360_depth_range(const float* depth, const float* acc, long long n, double ignore_frac, float near, float far,
+                       int auto_near, int auto_far, unsigned long long* work, float* range, mip360_stream_t stream);
+int mip360_visualize_depth(const float* depth, const float* acc, const float* range, int curve, float modulus,
+                           const float* lut, int n_lut, long long n, float* vis, uint8_t* vis8, mip360_stream_t stream);
+
 /* fused AdamW over one flat fp32 parameter tensor (train.py:38,63,81 — "next" row f3 of SURVEY §8):
  * decoupled weight decay, bias correction from `step` (1-based), optional bf16 re-cast of the weights */
 int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -60,6 +60,12 @@ SIGNATURES = {
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
     "mip360_to8b": [P, c_longlong, P, P],
+    "mip360_vis_partials_len": [],
+    "mip360_vis_work_len": [],
+    "mip360_normals_scaling": [P, c_int, c_int, P, P, P],
+    "mip360_visualize_normals": [P, P, P, c_int, c_int, P, P, P],
+    "mip360_depth_range": [P, P, c_longlong, c_double, c_float, c_float, c_int, c_int, P, P, P],
+    "mip360_visualize_depth": [P, P, P, c_int, c_float, P, c_int, c_longlong, P, P, P],
     "mip360_adamw": [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P],
 }
 _RESTYPES = {

@@ -24,6 +24,7 @@ SOURCES = {
     "composite.cu": ["--fmad=false"],
     "losses.cu": ["--fmad=false"],
     "raygen.cu": ["--fmad=false"],
+    "visualize.cu": ["--fmad=false"],
     "gemm_tcgen05.cu": [],
     "mlp_api.cu": [],
 }

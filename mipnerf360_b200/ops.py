@@ -507,3 +507,64 @@ def to8b(img):
     out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
     call("mip360_to8b", ptr(x), x.numel(), ptr(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# depth / normal visualisation of a rendered frame (intern/pose.py:112-212)
+# ---------------------------------------------------------------------------------------------------
+CURVES = {"neg_log": 0, "identity": 1, "inverse": 2, "log": 3}
+
+
+def normals_scaling(depth):
+    """pose.py:130-136: fp64 stats [count, mean x/y/z, var x/y/z, scaling] over the non-NaN pixels of depth [H,W]."""
+    d = f32c(depth)
+    check_cuda(d)
+    H, W = d.shape
+    lib = _lib.load()
+    partials = torch.empty(lib.mip360_vis_partials_len(), device=d.device, dtype=torch.float64)
+    stats = torch.zeros(8, device=d.device, dtype=torch.float64)
+    call("mip360_normals_scaling", ptr(d), H, W, ptr(partials), ptr(stats))
+    return stats
+
+
+def visualize_normals(depth, acc=None, stats=None, as_uint8=False):
+    """pose.py:128-147 on the device: [H,W,3] fp32 shading of the fake normals of depth, or its to8b image."""
+    d = f32c(depth)
+    check_cuda(d)
+    H, W = d.shape
+    a = None if acc is None else f32c(acc)
+    if stats is None:
+        stats = normals_scaling(d)
+    out = torch.empty((H, W, 3), device=d.device, dtype=torch.uint8 if as_uint8 else torch.float32)
+    call("mip360_visualize_normals", ptr(d), ptr(a), ptr(stats), H, W, None if as_uint8 else ptr(out),
+         ptr(out) if as_uint8 else None)
+    return out
+
+
+def depth_range(depth, acc=None, near=None, far=None, ignore_frac=0.0):
+    """pose.py:180-194: device tensor [near, far]; falsy near / far are replaced by the acc-weighted depth quantiles."""
+    d = f32c(depth)
+    check_cuda(d)
+    a = None if acc is None else f32c(acc)
+    auto_near, auto_far = not near, not far  # `near = near or ...` in the reference: 0 and None both mean automatic
+    lib = _lib.load()
+    work = torch.empty(lib.mip360_vis_work_len(), device=d.device, dtype=torch.int64)
+    rng = torch.empty(2, device=d.device, dtype=torch.float32)
+    call("mip360_depth_range", ptr(d), ptr(a), d.numel(), float(ignore_frac), float(near or 0.0), float(far or 0.0),
+         int(auto_near), int(auto_far), ptr(work), ptr(rng))
+    return rng
+
+
+def visualize_depth(depth, acc=None, near=None, far=None, ignore_frac=0.0, curve="neg_log", modulus=0.0, lut=None,
+                    as_uint8=False):
+    """pose.py:149-212 on the device.  lut: [n,3] fp32 colour table (listed-colour-map indexing); None with
+    modulus > 0 selects the sinebow map."""
+    d = f32c(depth)
+    check_cuda(d)
+    a = None if acc is None else f32c(acc)
+    rng = depth_range(d, a, near, far, ignore_frac)
+    table = None if lut is None else f32c(lut)[:, :3].contiguous()
+    out = torch.empty(tuple(d.shape) + (3,), device=d.device, dtype=torch.uint8 if as_uint8 else torch.float32)
+    call("mip360_visualize_depth", ptr(d), ptr(a), ptr(rng), CURVES[curve], float(modulus), ptr(table),
+         0 if table is None else table.shape[0], d.numel(), None if as_uint8 else ptr(out), ptr(out) if as_uint8 else None)
+    return out

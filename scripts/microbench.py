@@ -5,6 +5,8 @@
                                                            compositing, interlevel at N = 32/64/128, 1M..64M rays
     python scripts/microbench.py render  [--out f.json]    full-image inference: 1008x756 LLFF-shaped (NDC) and
                                                            4946x3286 garden-shaped unbounded poses, rays/s
+    python scripts/microbench.py visualize [--out f.json]  depth / normal pictures of a frame (pose.py:112-212) at both
+                                                           frame sizes: Mpixel/s and fraction of HBM peak
 
 Every number is CUDA-event time on the launching stream after 3 warm-up launches; inputs are far larger than L2.
 Achieved GB/s uses the ALGORITHMIC bytes of SURVEY §8d / BASELINE.md §4, not the measured traffic.
@@ -213,14 +215,46 @@ def render(out_path, chunks):
         dist.destroy_process_group()
 
 
+def visualize(out_path):
+    """§8f rank 4: frame post-processing.  Algorithmic bytes per pixel: depth 4 + acc 4 read, 3 written (uint8 picture);
+    the scaling statistics read depth twice (8 B); automatic planes read depth + acc in each of the 35 passes."""
+    pk = peak_hbm()
+    rows = []
+    for h, w in ((756, 1008), (3286, 4946)):
+        n = h * w
+        yy, xx = torch.meshgrid(torch.arange(h, device=DEV, dtype=torch.float32),
+                                torch.arange(w, device=DEV, dtype=torch.float32), indexing="ij")
+        depth = 3 + torch.sin(xx / 40) * torch.cos(yy / 55) + 0.02 * torch.randn(h, w, device=DEV)
+        acc = torch.rand(h, w, device=DEV)
+        lut = torch.rand(256, 3, device=DEV)
+        stats = ops.normals_scaling(depth)
+
+        def rec(name, ms, bytes_per_px):
+            gbs = bytes_per_px * n / ms / 1e6
+            rows.append(dict(kernel=name, h=h, w=w, ms=ms, mpix_s=n / ms / 1e3, bytes_per_pixel=bytes_per_px, gbs=gbs,
+                             frac_hbm=gbs / pk))
+            print(f"{name:28s} {h}x{w}  {ms:8.4f} ms  {n / ms / 1e3:10.1f} Mpix/s  {gbs:8.1f} GB/s  {gbs / pk:.3f}")
+
+        rec("normals_scaling", timeit(lambda: ops.normals_scaling(depth)), 8)
+        rec("visualize_normals_u8", timeit(lambda: ops.visualize_normals(depth, acc, stats=stats, as_uint8=True)), 11)
+        rec("visualize_normals_f32", timeit(lambda: ops.visualize_normals(depth, acc, stats=stats)), 20)
+        rec("visualize_depth_u8", timeit(lambda: ops.visualize_depth(depth, acc, 2.0, 4.5, lut=lut, as_uint8=True)), 11)
+        rec("visualize_depth_sinebow_u8", timeit(lambda: ops.visualize_depth(depth, acc, 2.0, 4.5, modulus=0.25, as_uint8=True)), 11)
+        rec("depth_range_auto_frac0", timeit(lambda: ops.depth_range(depth, acc, None, None, 0.0)), 4)
+        rec("depth_range_auto_frac0.05", timeit(lambda: ops.depth_range(depth, acc, None, None, 0.05)), 8 * 34 + 4)
+        rgb = torch.rand(h, w, 3, device=DEV)
+        rec("to8b_rgb", timeit(lambda: ops.to8b(rgb)), 15)
+    json.dump(dict(peak_hbm_gbs=pk, rows=rows), open(out_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["micro", "render"])
+    ap.add_argument("mode", choices=["micro", "render", "visualize"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--chunks", type=int, default=65536)
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out = a.out or os.path.join(ROOT, "gpurun_out", f"{a.mode}.json")
     t0 = time.time()
-    micro(out) if a.mode == "micro" else render(out, a.chunks)
+    micro(out) if a.mode == "micro" else render(out, a.chunks) if a.mode == "render" else visualize(out)
     print(f"wrote {out} in {time.time() - t0:.1f} s")
