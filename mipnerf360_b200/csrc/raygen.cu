@@ -102,11 +102,29 @@ raygen_kernel(const RayGenParams p, float* __restrict__ origins, float* __restri
 }
 
 // intern/utils.py:17-21 (to8b): (255 * clip(nan_to_num(x), 0, 1)).astype(uint8) — truncation, as NumPy's cast
-__global__ void __launch_bounds__(256) to8b_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = fminf(fmaxf(nan_to_num_f(x[i]), 0.f), 1.f);
-  out[i] = (uint8_t)(255.f * v);
+__device__ __forceinline__ uint32_t to8b_one(float x) {
+  return (uint32_t)(uint8_t)(255.f * fminf(fmaxf(nan_to_num_f(x), 0.f), 1.f));
+}
+// 16 values per thread: four 16-byte loads, one 16-byte store (scalar tail / unaligned buffers: one value per thread)
+__global__ void __launch_bounds__(256) to8b_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out,
+                                                   int vec) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long i0 = t * 16;
+    if (i0 + 16 <= n) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i0 + 4 * j);
+        w[j] = to8b_one(v.x) | (to8b_one(v.y) << 8) | (to8b_one(v.z) << 16) | (to8b_one(v.w) << 24);
+      }
+      *reinterpret_cast<uint4*>(out + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (long long i = i0; i < n; ++i) out[i] = (uint8_t)to8b_one(x[i]);
+    }
+  } else if (t < n) {
+    out[t] = (uint8_t)to8b_one(x[t]);
+  }
 }
 
 }  // namespace mip360
@@ -116,7 +134,9 @@ using namespace mip360;
 extern "C" int mip360_to8b(const float* x, long long n, uint8_t* out, mip360_stream_t stream) {
   MIP_REQUIRE(n <= 0 || (x && out), "to8b: null pointer");
   if (n <= 0) return MIP360_OK;
-  to8b_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long threads = vec ? (n + 15) / 16 : n;
+  to8b_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, out, vec);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

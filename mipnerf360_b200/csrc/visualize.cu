@@ -81,52 +81,85 @@ __global__ void __launch_bounds__(32) depth_moments_reduce_kernel(const double* 
   }
 }
 
+// Pictures are written four pixels per thread: 12 bytes (uint8) or 48 bytes (fp32) of RGB per thread go out as
+// three 32-bit / 128-bit stores instead of twelve byte / word stores.
+constexpr int VIS_PPT = 4;
+
+__device__ __forceinline__ void store_rgb4(float* __restrict__ vis, uint8_t* __restrict__ vis8, long long i0, long long n,
+                                           const float (&v)[VIS_PPT][3], const uint8_t (&b)[VIS_PPT][3]) {
+  if (i0 + VIS_PPT <= n) {
+    if (vis) {
+      float4* o = reinterpret_cast<float4*>(vis + 3 * i0);  // 48-byte groups: 16-byte aligned with the tensor
+      o[0] = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
+      o[1] = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
+      o[2] = make_float4(v[2][2], v[3][0], v[3][1], v[3][2]);
+    }
+    if (vis8) {
+      uint32_t* o = reinterpret_cast<uint32_t*>(vis8 + 3 * i0);
+      o[0] = b[0][0] | (b[0][1] << 8) | (b[0][2] << 16) | ((uint32_t)b[1][0] << 24);
+      o[1] = b[1][1] | (b[1][2] << 8) | (b[2][0] << 16) | ((uint32_t)b[2][1] << 24);
+      o[2] = b[2][2] | (b[3][0] << 8) | (b[3][1] << 16) | ((uint32_t)b[3][2] << 24);
+    }
+  } else {
+    for (int p = 0; p < VIS_PPT && i0 + p < n; ++p)
+      for (int c = 0; c < 3; ++c) {
+        if (vis) vis[3 * (i0 + p) + c] = v[p][c];
+        if (vis8) vis8[3 * (i0 + p) + c] = b[p][c];
+      }
+  }
+}
+
 // pose.py:112-121 (depth_to_normals on scaling * depth) + :138-145 (shading, white where nothing accumulated)
 __global__ void __launch_bounds__(VIS_THREADS) normals_kernel(const float* __restrict__ depth, const float* __restrict__ acc,
                                                                const double* __restrict__ stats, int H, int W,
                                                                float* __restrict__ vis, uint8_t* __restrict__ vis8) {
   const long long n = (long long)H * W;
-  const long long i = (long long)blockIdx.x * VIS_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const int x = (int)(i % W), y = (int)(i / W);
+  const long long i0 = ((long long)blockIdx.x * VIS_THREADS + threadIdx.x) * VIS_PPT;
+  if (i0 >= n) return;
   const double sc = stats[7];
-  double z[3][3];
+  float vf[VIS_PPT][3];
+  uint8_t vb[VIS_PPT][3];
 #pragma unroll
-  for (int dy = -1; dy <= 1; ++dy)
+  for (int p = 0; p < VIS_PPT; ++p) {
+    const long long i = i0 + p < n ? i0 + p : n - 1;
+    const int x = (int)(i % W), y = (int)(i / W);
+    double z[3][3];
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int yy = y + dy, xx = x + dx;
-      z[dy + 1][dx + 1] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? sc * (double)__ldg(depth + (long long)yy * W + xx) : 0.0;
-    }
-  // true convolution (kernel flipped): out = sum_ij k[i][j] z[2-i][2-j] with k_dy = edge (rows) x blur (cols) and
-  // k_dx = blur (rows) x edge (cols).  The zero taps are kept: 0 * NaN = NaN, so a NaN depth poisons its whole 3x3
-  // neighbourhood in both derivatives, exactly as scipy's convolve2d does.
-  const double fe[3] = {-0.5, 0.0, 0.5}, fb[3] = {0.25, 0.5, 0.25};
-  double gy = 0.0, gx = 0.0;
+    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        z[dy + 1][dx + 1] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? sc * (double)__ldg(depth + (long long)yy * W + xx) : 0.0;
+      }
+    // true convolution (kernel flipped): out = sum_ij k[i][j] z[2-i][2-j] with k_dy = edge (rows) x blur (cols) and
+    // k_dx = blur (rows) x edge (cols).  The zero taps are kept: 0 * NaN = NaN, so a NaN depth poisons its whole 3x3
+    // neighbourhood in both derivatives, exactly as scipy's convolve2d does.
+    const double fe[3] = {-0.5, 0.0, 0.5}, fb[3] = {0.25, 0.5, 0.25};
+    double gy = 0.0, gx = 0.0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      gy += (fb[j] * fe[i]) * z[2 - i][2 - j];
-      gx += (fb[i] * fe[j]) * z[2 - i][2 - j];
-    }
-  const double inv = 1.0 / sqrt(1.0 + gx * gx + gy * gy);
-  const double nrm[3] = {gx * inv, gy * inv, inv};
-  // pose.py:143: vis * acc + (1 - acc) — (1 - acc) is formed in float32 (acc's dtype), then promoted
-  const double a = acc ? (double)acc[i] : 1.0, one_minus_a = acc ? (double)(1.f - acc[i]) : 0.0;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double v = (nrm[c] + 1.0) * 0.5;
-    if (isnan(nrm[c])) v = 1.0;  // isnan(normals) + nan_to_num(...): NaN -> 1 + 0
-    else if (isinf(v)) v = v > 0 ? DBL_MAX : -DBL_MAX;
-    if (acc) v = v * a + one_minus_a;
-    if (vis) vis[3 * i + c] = (float)v;
-    if (vis8) {
+      for (int j = 0; j < 3; ++j) {
+        gy += (fb[j] * fe[r]) * z[2 - r][2 - j];
+        gx += (fb[r] * fe[j]) * z[2 - r][2 - j];
+      }
+    const double inv = 1.0 / sqrt(1.0 + gx * gx + gy * gy);
+    const double nrm[3] = {gx * inv, gy * inv, inv};
+    // pose.py:143: vis * acc + (1 - acc) — (1 - acc) is formed in float32 (acc's dtype), then promoted
+    const double a = acc ? (double)acc[i] : 1.0, one_minus_a = acc ? (double)(1.f - acc[i]) : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double v = (nrm[c] + 1.0) * 0.5;
+      if (isnan(nrm[c])) v = 1.0;  // isnan(normals) + nan_to_num(...): NaN -> 1 + 0
+      else if (isinf(v)) v = v > 0 ? DBL_MAX : -DBL_MAX;
+      if (acc) v = v * a + one_minus_a;
+      vf[p][c] = (float)v;
       double u = isnan(v) ? 0.0 : v;
       u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
-      vis8[3 * i + c] = (uint8_t)(255.0 * u);
+      vb[p][c] = (uint8_t)(255.0 * u);
     }
   }
+  store_rgb4(vis, vis8, i0, n, vf, vb);
 }
 
 // ---- depth: automatic near / far ----------------------------------------------------------------
@@ -141,10 +174,8 @@ __device__ __forceinline__ float key_depth(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
 // acc in exact integer units of 2^-24; pixels with NaN depth carry no weight (pose.py:178)
-__device__ __forceinline__ unsigned long long depth_weight(float z, const float* acc, long long i) {
-  if (isnan(z)) return 0ull;
-  float a = acc ? acc[i] : 1.f;
-  if (!(a > 0.f)) return 0ull;
+__device__ __forceinline__ unsigned long long depth_weight(float z, float a) {
+  if (isnan(z) || !(a > 0.f)) return 0ull;
   return __float2ull_rn(fminf(a, 1024.f) * 16777216.f);
 }
 
@@ -188,18 +219,39 @@ __global__ void __launch_bounds__(VIS_THREADS) depth_quantile_kernel(const float
   unsigned long long s_lo = 0ull, s_hi = 0ull;
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   bool any_max = false;
-  for (long long i = (long long)blockIdx.x * VIS_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * VIS_THREADS) {
-    const float z = depth[i];
+  auto visit = [&](float z, float a) {
     const uint32_t k = depth_key(z);
     if (step < 32) {
-      const unsigned long long w = depth_weight(z, acc, i);
+      const unsigned long long w = depth_weight(z, a);
       if (k <= q.c_lo) s_lo += w;
       if (k <= q.c_hi) s_hi += w;
     } else {
       if (k >= q.k_lo && k < kmin) kmin = k;
       if (k <= q.k_hi && k >= kmax) { kmax = k; any_max = true; }
     }
+  };
+  const long long tid = (long long)blockIdx.x * VIS_THREADS + threadIdx.x, nthr = (long long)gridDim.x * VIS_THREADS;
+  long long done = 0;
+  if (((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(acc)) & 15) == 0) {
+    const long long n4 = n / 4;  // 16-byte loads, two groups in flight per thread
+    const float4* d4 = reinterpret_cast<const float4*>(depth);
+    const float4* a4 = reinterpret_cast<const float4*>(acc);
+    const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+    long long g = tid;
+    for (; g + nthr < n4; g += 2 * nthr) {
+      const float4 z0 = d4[g], z1 = d4[g + nthr];
+      const float4 w0 = acc ? a4[g] : ones, w1 = acc ? a4[g + nthr] : ones;
+      visit(z0.x, w0.x); visit(z0.y, w0.y); visit(z0.z, w0.z); visit(z0.w, w0.w);
+      visit(z1.x, w1.x); visit(z1.y, w1.y); visit(z1.z, w1.z); visit(z1.w, w1.w);
+    }
+    for (; g < n4; g += nthr) {
+      const float4 z0 = d4[g];
+      const float4 w0 = acc ? a4[g] : ones;
+      visit(z0.x, w0.x); visit(z0.y, w0.y); visit(z0.z, w0.z); visit(z0.w, w0.w);
+    }
+    done = n4 * 4;
   }
+  for (long long i = done + tid; i < n; i += nthr) visit(depth[i], acc ? acc[i] : 1.f);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (step < 32) {
 #pragma unroll
@@ -266,39 +318,62 @@ __global__ void __launch_bounds__(VIS_THREADS) depth_vis_kernel(const float* __r
                                                                  const float* __restrict__ range, int curve, float modulus,
                                                                  const float* __restrict__ lut, int n_lut, long long n,
                                                                  float* __restrict__ vis, uint8_t* __restrict__ vis8) {
-  const long long i = (long long)blockIdx.x * VIS_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const float z = depth[i];
-  float a = acc ? acc[i] : 1.f;
-  if (isnan(z)) a = 0.f;  // pose.py:178
-  const float d = curve_f(z, curve), cn = curve_f(range[0], curve), cf = curve_f(range[1], curve);
-  float value;
-  if (modulus > 0.f) {
-    float r = fmodf(d, modulus);  // np.mod: result takes the sign of the divisor
-    if (r != 0.f && r < 0.f) r += modulus;
-    value = r / modulus;
+  const long long i0 = ((long long)blockIdx.x * VIS_THREADS + threadIdx.x) * VIS_PPT;
+  if (i0 >= n) return;
+  const float cn = curve_f(range[0], curve), cf = curve_f(range[1], curve);
+  const float lo = (isnan(cn) || isnan(cf)) ? __uint_as_float(0x7FC00000u) : fminf(cn, cf);  // np.minimum propagates NaN
+  const float span = fabsf(cf - cn);
+  float zs[VIS_PPT], as[VIS_PPT];
+  if (i0 + VIS_PPT <= n && ((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(acc)) & 15) == 0) {
+    const float4 z4 = *reinterpret_cast<const float4*>(depth + i0);
+    zs[0] = z4.x; zs[1] = z4.y; zs[2] = z4.z; zs[3] = z4.w;
+    if (acc) {
+      const float4 a4 = *reinterpret_cast<const float4*>(acc + i0);
+      as[0] = a4.x; as[1] = a4.y; as[2] = a4.z; as[3] = a4.w;
+    }
   } else {
-    const float lo = (isnan(cn) || isnan(cf)) ? __uint_as_float(0x7FC00000u) : fminf(cn, cf);  // np.minimum propagates NaN
-    value = (d - lo) / fabsf(cf - cn);
-    value = isnan(value) ? 0.f : fminf(fmaxf(value, 0.f), 1.f);  // nan_to_num(clip(., 0, 1))
-  }
-  float rgb[3];
-  if (lut) {
-    // a listed colour map called with floats: index = trunc(value * N), value == 1 -> N - 1
-    int idx = isnan(value) ? 0 : (int)(value * (float)n_lut);
-    idx = idx < 0 ? 0 : (idx >= n_lut ? n_lut - 1 : idx);
-    rgb[0] = __ldg(lut + 3 * idx); rgb[1] = __ldg(lut + 3 * idx + 1); rgb[2] = __ldg(lut + 3 * idx + 2);
-  } else {
-    rgb[0] = sinebow_f(0.5f - value);
-    rgb[1] = sinebow_f(0.833333313465118408f - value);
-    rgb[2] = sinebow_f(1.16666662693023682f - value);
-  }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float v = rgb[c] * a + (1.f - a);
-    if (vis) vis[3 * i + c] = v;
-    if (vis8) vis8[3 * i + c] = to8b_f(v);
+    for (int p = 0; p < VIS_PPT; ++p) {
+      const long long i = i0 + p < n ? i0 + p : n - 1;
+      zs[p] = depth[i];
+      if (acc) as[p] = acc[i];
+    }
   }
+  float vf[VIS_PPT][3];
+  uint8_t vb[VIS_PPT][3];
+#pragma unroll
+  for (int p = 0; p < VIS_PPT; ++p) {
+    const float z = zs[p];
+    float a = acc ? as[p] : 1.f;
+    if (isnan(z)) a = 0.f;  // pose.py:178
+    const float d = curve_f(z, curve);
+    float value;
+    if (modulus > 0.f) {
+      float r = fmodf(d, modulus);  // np.mod: result takes the sign of the divisor
+      if (r != 0.f && r < 0.f) r += modulus;
+      value = r / modulus;
+    } else {
+      value = (d - lo) / span;
+      value = isnan(value) ? 0.f : fminf(fmaxf(value, 0.f), 1.f);  // nan_to_num(clip(., 0, 1))
+    }
+    float rgb[3];
+    if (lut) {
+      // a listed colour map called with floats: index = trunc(value * N), value == 1 -> N - 1
+      int idx = isnan(value) ? 0 : (int)(value * (float)n_lut);
+      idx = idx < 0 ? 0 : (idx >= n_lut ? n_lut - 1 : idx);
+      rgb[0] = __ldg(lut + 3 * idx); rgb[1] = __ldg(lut + 3 * idx + 1); rgb[2] = __ldg(lut + 3 * idx + 2);
+    } else {
+      rgb[0] = sinebow_f(0.5f - value);
+      rgb[1] = sinebow_f(0.833333313465118408f - value);
+      rgb[2] = sinebow_f(1.16666662693023682f - value);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vf[p][c] = rgb[c] * a + (1.f - a);
+      vb[p][c] = to8b_f(vf[p][c]);
+    }
+  }
+  store_rgb4(vis, vis8, i0, n, vf, vb);
 }
 
 }  // namespace mip360
@@ -331,7 +406,8 @@ int mip360_visualize_normals(const float* depth, const float* acc, const double*
   const long long n = (long long)H * W;
   if (n == 0) return MIP360_OK;
   MIP_REQUIRE(depth && stats && (vis || vis8), "visualize_normals: null pointer");
-  normals_kernel<<<(int)((n + VIS_THREADS - 1) / VIS_THREADS), VIS_THREADS, 0, (cudaStream_t)stream>>>(depth, acc, stats, H, W, vis, vis8);
+  MIP_REQUIRE((reinterpret_cast<uintptr_t>(vis) & 15) == 0 && (reinterpret_cast<uintptr_t>(vis8) & 3) == 0, "visualize_normals: vis must be 16-byte and vis8 4-byte aligned");
+  normals_kernel<<<(int)((n + VIS_THREADS * VIS_PPT - 1) / (VIS_THREADS * VIS_PPT)), VIS_THREADS, 0, (cudaStream_t)stream>>>(depth, acc, stats, H, W, vis, vis8);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -364,9 +440,10 @@ int mip360_visualize_depth(const float* depth, const float* acc, const float* ra
   MIP_REQUIRE(n >= 0, "visualize_depth: bad size");
   if (n == 0) return MIP360_OK;
   MIP_REQUIRE(depth && range && (vis || vis8), "visualize_depth: null pointer");
+  MIP_REQUIRE((reinterpret_cast<uintptr_t>(vis) & 15) == 0 && (reinterpret_cast<uintptr_t>(vis8) & 3) == 0, "visualize_depth: vis must be 16-byte and vis8 4-byte aligned");
   MIP_REQUIRE(curve >= 0 && curve <= 3, "visualize_depth: curve=%d", curve);
   MIP_REQUIRE(!lut || n_lut >= 1, "visualize_depth: empty colour table");
-  depth_vis_kernel<<<(int)((n + VIS_THREADS - 1) / VIS_THREADS), VIS_THREADS, 0, (cudaStream_t)stream>>>(
+  depth_vis_kernel<<<(int)((n + VIS_THREADS * VIS_PPT - 1) / (VIS_THREADS * VIS_PPT)), VIS_THREADS, 0, (cudaStream_t)stream>>>(
       depth, acc, range, curve, modulus, lut, n_lut, n, vis, vis8);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;

@@ -153,6 +153,15 @@ def test_gpu_visualisers_properties_and_errors(pose):
     # uint8 output equals to8b of the float output
     from mipnerf360_b200 import ops
     assert torch.equal(pose.visualize_depth(depth, acc, 2.0, 6.0, as_uint8=True), ops.to8b(out))
+    # buffers that are contiguous but not 16-byte aligned take the scalar-load path: same pictures
+    flat_d, flat_a = torch.cat([depth.flatten(), depth.new_zeros(4)]), torch.cat([acc.flatten(), acc.new_zeros(4)])
+    d1 = flat_d.roll(1)[1:1 + depth.numel()].view_as(depth)
+    a1 = flat_a.roll(1)[1:1 + acc.numel()].view_as(acc)
+    assert d1.data_ptr() % 16 == 4 and torch.equal(d1, depth)
+    assert torch.equal(pose.visualize_depth(d1, a1, 2.0, 6.0), out)
+    assert torch.equal(ops.depth_range(d1, a1, None, None, 0.1), ops.depth_range(depth, acc, None, None, 0.1))
+    x = torch.randn(1001, device="cuda", generator=g)
+    assert torch.equal(ops.to8b(x.roll(1)[1:]), ops.to8b(x[:-1].clone()))
     with pytest.raises(TypeError):
         pose.visualize_depth(depth, acc, 2.0, 6.0, curve_fn=lambda x: x)
     with pytest.raises(TypeError):
