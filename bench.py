@@ -117,7 +117,8 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       os.environ.get("MIP360_SMI_MS", "100"), "-i", str(index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 

@@ -214,30 +214,57 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
 template <int E>
 struct RgRay {
   float t[E + 1], sigma[E], aux[E], delta[E], dd[E], T[E], w[E];
+  float c[E][3];  // colours (only filled when wanted)
+  float d[3];     // ray direction
 };
 
-// loads knots + densities (+ activation), forms the weights of the lane's E intervals
+// Every global load of the lane is issued here, before any arithmetic: the activation code below branches
+// (softplus threshold, log1pf), and loads placed after a branch would start a second round trip to memory.
 template <int E>
-__device__ __forceinline__ void rg_weights(RgRay<E>& r, const float* __restrict__ rgb_or_raw,
-                                           const float* __restrict__ density, const float* __restrict__ t_vals,
-                                           const float* __restrict__ dirs, long long ray, int N, int gl, int head_mode,
-                                           int density_mode, float density_bias) {
+__device__ __forceinline__ void rg_fetch(RgRay<E>& r, const float* __restrict__ rgb_or_raw,
+                                         const float* __restrict__ density, const float* __restrict__ t_vals,
+                                         const float* __restrict__ dirs, long long ray, int N, int gl, int head_mode,
+                                         bool want_rgb, float rgb_padding) {
   const int j0 = gl * E;
   rg_load_knots<E>(t_vals + ray * (N + 1), j0, r.t);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r.d[i] = __ldg(dirs + ray * 3 + i);
   if (head_mode == 1) {
+    // one 16-byte load per sample: density logit and colour together (whole sectors, a single pass over the rows)
     const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + ray * N + j0;
+    const float scale = 1.f + 2.f * rgb_padding;
+    float4 v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = __ldg(raw4 + i);
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-      r.aux[i] = __ldg(raw4 + i).x;
-      r.sigma[i] = softplus_f(r.aux[i] + density_bias);
+      r.aux[i] = v[i].x;
+      if (want_rgb) {
+        r.c[i][0] = v[i].y * scale - rgb_padding;
+        r.c[i][1] = v[i].z * scale - rgb_padding;
+        r.c[i][2] = v[i].w * scale - rgb_padding;
+      }
     }
   } else {
     rg_load<E>(density + ray * N + j0, r.aux);
+    if (want_rgb) {
+      float flat[3 * E];
+      rg_load<3 * E>(rgb_or_raw + (ray * N + j0) * 3, flat);
 #pragma unroll
-    for (int i = 0; i < E; ++i) r.sigma[i] = density_mode == 1 ? softplus_f(r.aux[i] + density_bias) : r.aux[i];
+      for (int i = 0; i < E; ++i) {
+        r.c[i][0] = flat[3 * i]; r.c[i][1] = flat[3 * i + 1]; r.c[i][2] = flat[3 * i + 2];
+      }
+    }
   }
-  const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
-  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// density activation, then the weights of the lane's E intervals
+template <int E>
+__device__ __forceinline__ void rg_weights(RgRay<E>& r, int gl, int head_mode, int density_mode, float density_bias) {
+#pragma unroll
+  for (int i = 0; i < E; ++i)
+    r.sigma[i] = (head_mode == 1 || density_mode == 1) ? softplus_f(r.aux[i] + density_bias) : r.aux[i];
+  const float dnorm = sqrtf(r.d[0] * r.d[0] + r.d[1] * r.d[1] + r.d[2] * r.d[2]);
   float run = 0.f, excl[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
@@ -254,55 +281,33 @@ __device__ __forceinline__ void rg_weights(RgRay<E>& r, const float* __restrict_
   }
 }
 
-template <int E>
-__device__ __forceinline__ void rg_load_rgb(float (&c)[E][3], const float* __restrict__ rgb_or_raw, long long ray, int N,
-                                            int j0, int head_mode, float rgb_padding) {
-  if (head_mode == 1) {
-    const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + ray * N + j0;
-    const float scale = 1.f + 2.f * rgb_padding;
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      const float4 v = __ldg(raw4 + i);
-      c[i][0] = v.y * scale - rgb_padding;
-      c[i][1] = v.z * scale - rgb_padding;
-      c[i][2] = v.w * scale - rgb_padding;
-    }
-  } else {
-    float flat[3 * E];
-    rg_load<3 * E>(rgb_or_raw + (ray * N + j0) * 3, flat);
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      c[i][0] = flat[3 * i]; c[i][1] = flat[3 * i + 1]; c[i][2] = flat[3 * i + 2];
-    }
-  }
-}
-
-template <int E>
+// WO = weights-only (density_to_weight): a separate instantiation, so the colour registers do not cost it occupancy
+template <int E, bool WO>
 __global__ void __launch_bounds__(RG_THREADS)
 composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                         const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
-                        int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                        int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                         float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
                         float* __restrict__ weights) {
   constexpr int N = E * RG_LANES;
+  constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
     const long long ray_raw = base + (threadIdx.x >> 3);
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
-    rg_weights<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, density_mode, density_bias);
+    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
+    rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
     if (weights && active) rg_store<E>(weights + ray * N + j0, r.w);
     if (weights_only) continue;
-    float c[E][3];
-    rg_load_rgb<E>(c, rgb_or_raw, ray, N, j0, head_mode, rgb_padding);
     float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       a += r.w[i];
-      cr += r.w[i] * c[i][0];
-      cg += r.w[i] * c[i][1];
-      cb += r.w[i] * c[i][2];
+      cr += r.w[i] * r.c[i][0];
+      cg += r.w[i] * r.c[i][1];
+      cb += r.w[i] * r.c[i][2];
       wt += r.w[i] * (0.5f * (r.t[i] + r.t[i + 1]));
     }
     a = rg_sum(a); cr = rg_sum(cr); cg = rg_sum(cg); cb = rg_sum(cb); wt = rg_sum(wt);
@@ -324,14 +329,15 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
   }
 }
 
-template <int E>
+template <int E, bool WO>
 __global__ void __launch_bounds__(RG_THREADS)
 composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                         const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
-                        int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
+                        int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                         const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
                         float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw) {
   constexpr int N = E * RG_LANES;
+  constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
   const float cscale = 1.f + 2.f * rgb_padding;
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
@@ -339,14 +345,11 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
-    rg_weights<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, density_mode, density_bias);
-    float c[E][3];
+    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
     float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
     if (!weights_only) {
-      rg_load_rgb<E>(c, rgb_or_raw, ray, N, j0, head_mode, rgb_padding);
       if (g_rgb) { gr = __ldg(g_rgb + ray * 3); gg = __ldg(g_rgb + ray * 3 + 1); gb = __ldg(g_rgb + ray * 3 + 2); }
       if (g_acc) ga = __ldg(g_acc + ray);
-      if (white_bkgd) ga -= (gr + gg + gb);
     }
     float G[E];
     if (g_w) {
@@ -355,11 +358,14 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
 #pragma unroll
       for (int i = 0; i < E; ++i) G[i] = 0.f;
     }
+    // all loads are in flight; arithmetic starts here
+    rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
+    if (!weights_only && white_bkgd) ga -= (gr + gg + gb);
     float run = 0.f, excl_rev[E];
 #pragma unroll
     for (int i = E - 1; i >= 0; --i) {
       G[i] += ga;
-      if (!weights_only) G[i] += gr * c[i][0] + gg * c[i][1] + gb * c[i][2];
+      if (!weights_only) G[i] += gr * r.c[i][0] + gg * r.c[i][1] + gb * r.c[i][2];
       excl_rev[i] = run;
       run += G[i] * r.w[i];
     }
@@ -397,17 +403,17 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
   }
 }
 
-template <typename... Args>
+template <bool WO, typename... Args>
 static void launch_composite_fwd(int N, int B, cudaStream_t st, Args... a) {
-  if (N == 32) composite_fwd_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
-  else if (N == 64) composite_fwd_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
-  else composite_fwd_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  if (N == 32) composite_fwd_rg_kernel<4, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else if (N == 64) composite_fwd_rg_kernel<8, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else composite_fwd_rg_kernel<16, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
 }
-template <typename... Args>
+template <bool WO, typename... Args>
 static void launch_composite_bwd(int N, int B, cudaStream_t st, Args... a) {
-  if (N == 32) composite_bwd_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
-  else if (N == 64) composite_bwd_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
-  else composite_bwd_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  if (N == 32) composite_bwd_rg_kernel<4, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else if (N == 64) composite_bwd_rg_kernel<8, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
+  else composite_bwd_rg_kernel<16, WO><<<rg_grid(B), RG_THREADS, 0, st>>>(a...);
 }
 
 // intern/parameterization.py:5-8 with the eps shifts a single reference call observes (App. A4)
@@ -486,7 +492,7 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
-    launch_composite_fwd(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
+    launch_composite_fwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
                          rgb_padding, white_bkgd, comp_rgb, distance, acc, weights);
   else
     composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
@@ -505,7 +511,7 @@ int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const fl
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
-    launch_composite_bwd(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
+    launch_composite_bwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
                          rgb_padding, white_bkgd, g_rgb, g_acc, g_w, g_rgb_in, g_density, g_raw);
   else
     composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
@@ -521,7 +527,7 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
-    launch_composite_fwd(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
+    launch_composite_fwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
                          density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights);
   else
     composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
@@ -538,7 +544,7 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "density_to_weight_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
-    launch_composite_bwd(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
+    launch_composite_bwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
                          density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, g_w, (float*)nullptr,
                          g_density, (float*)nullptr);
   else

@@ -5,6 +5,7 @@
 // Compiled with --fmad=false: every fp32 operation is rounded the way the reference's unfused
 // PyTorch elementwise ops round it (reference: intern/parameterization.py, intern/encoding.py).
 #include "common.cuh"
+#include "ray_group.cuh"
 
 namespace mip360 {
 
@@ -307,6 +308,42 @@ frustum_norm_sq_kernel(const float* __restrict__ t0p, const float* __restrict__ 
   }
 }
 
+// The same sum for knot rows [B, N+1] with N in {32, 64, 128}: 8 lanes per ray, E = N/8 intervals per lane, so a
+// knot is fetched once per lane instead of twice per sample, the direction once per lane, and one fp64 add per
+// sample (the three fp32 squares of a sample are summed in fp32 first) replaces three.
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+frustum_norm_sq_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ directions, int B,
+                          double* __restrict__ out) {
+  constexpr int N = E * RG_LANES;
+  const int gl = threadIdx.x & 7;
+  double acc = 0.0;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray = base + (threadIdx.x >> 3);
+    if (ray >= B) continue;
+    float t[E + 1];
+    rg_load_knots<E>(t_vals + ray * (N + 1), gl * E, t);
+    const float d0 = __ldg(directions + ray * 3), d1 = __ldg(directions + ray * 3 + 1), d2 = __ldg(directions + ray * 3 + 2);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float mu = (t[i] + t[i + 1]) / 2.f, hw = (t[i + 1] - t[i]) / 2.f;
+      const float hw2 = hw * hw;
+      const float t_mean = mu + (2.f * mu * hw2) / (3.f * (mu * mu) + hw2);
+      const float m0 = d0 * t_mean, m1 = d1 * t_mean, m2 = d2 * t_mean;
+      acc += (double)(m0 * m0 + m1 * m1 + m2 * m2);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ double sm[RG_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < RG_THREADS / 32; ++i) s += sm[i];
+    atomicAdd(out, s);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sum_sq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
   double acc = 0.0;
@@ -462,8 +499,14 @@ int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const
   MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "frustum_norm_sq: bad sizes");
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
-  frustum_norm_sq_kernel<<<capped_blocks(S, 256), 256, 0, (cudaStream_t)stream>>>(t0, t1, t_stride, directions, S, N,
-                                                                                  div_magic(N), norm_sq);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rg_supported_host(N) && t1 == t0 + 1 && t_stride == N + 1) {  // adjacent knots of one [B, N+1] array
+    if (N == 32) frustum_norm_sq_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t0, directions, B, norm_sq);
+    else if (N == 64) frustum_norm_sq_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t0, directions, B, norm_sq);
+    else frustum_norm_sq_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t0, directions, B, norm_sq);
+  } else {
+    frustum_norm_sq_kernel<<<capped_blocks(S, 256), 256, 0, st>>>(t0, t1, t_stride, directions, S, N, div_magic(N), norm_sq);
+  }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -307,6 +307,15 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     if (gl == 0) tfs[rg_skew_l<E>(N)] = __ldg(tfrow + N);
     float w[E];
     rg_load<E>(w_fine + ray * N + j0, w);
+    // the coarse knots are fetched now, together with the fine row, so that the searches below do not start a
+    // second round trip to memory
+    const float* tc = t_coarse + ray * K;
+    float L[E], R[E];
+#pragma unroll
+    for (int c = 0; c < E; ++c) {
+      L[c] = __ldg(tc + gl + RG_LANES * c);
+      R[c] = __ldg(tc + gl + RG_LANES * c + 1);
+    }
     double run = 0.0, ex[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
@@ -329,14 +338,9 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
       endF[l] = tfs[rg_skew_l<E>((l + 1) * E)];
       endR[l] = tfs[rg_skew_l<E>((l + 1) * E - 1)];
     }
-    const float* tc = t_coarse + ray * K;
-    float L[E], R[E];
     int first[E], nR[E], baseF[E], baseR[E];
 #pragma unroll
     for (int c = 0; c < E; ++c) {
-      const int i = gl + RG_LANES * c;
-      L[c] = __ldg(tc + i);
-      R[c] = __ldg(tc + i + 1);
       int nf = 0, nr = 0;
 #pragma unroll
       for (int l = 0; l < RG_LANES; ++l) {

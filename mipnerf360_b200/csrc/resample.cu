@@ -223,6 +223,13 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
 #pragma unroll
     for (int c = 0; c < E; ++c) bins[rg_skew<E>(gl + RG_LANES * c)] = __ldg(trow + gl + RG_LANES * c);
     if (gl == 0) bins[rg_skew<E>(N)] = __ldg(trow + N);
+    // the jitter row is fetched now, with the weights and knots, not after the CDF has been built (a load issued
+    // behind the scan would cost a second round trip to memory)
+    float jit[E + 1];
+    if (jitter) {
+#pragma unroll
+      for (int c = 0; c <= E; ++c) jit[c] = __ldg(jitter + ray * K + ((c < E) ? gl + RG_LANES * c : N));
+    }
     if (blur) {
       float wl = __shfl_up_sync(FULL_MASK, w[E - 1], 1, RG_LANES);
       float wr = __shfl_down_sync(FULL_MASK, w[0], 1, RG_LANES);
@@ -286,7 +293,7 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
       const int m = (c < E) ? gl + RG_LANES * c : N;
       u[c] = __ldg(u_base + m);
       if (jitter) {
-        u[c] = (u[c] + u[c]) + __ldg(jitter + ray * K + m);  // the doubled stratum offset is the reference's (App. A5)
+        u[c] = (u[c] + u[c]) + jit[c];  // the doubled stratum offset is the reference's (App. A5)
         u[c] = fminf(u[c], one_m_eps);
       }
       int nfull = 0;
