@@ -47,6 +47,35 @@ def test_ctypes_table_matches_header(lib_path):
     assert lib.mip360_partials_len(16) >= 1024
 
 
+def test_header_is_plain_c_and_a_c_program_links(lib_path, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++-isms, no torch types) and a C translation unit
+    that includes it links against the library and calls it (no device needed for these calls)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-Werror", HEADER], check=True)
+    src = tmp_path / "abi_demo.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "mip360_b200.h"\n'
+        "int main(void) {\n"
+        "  struct mip360_layer l; memset(&l, 0, sizeof l);\n"
+        "  if (mip360_version() != 100) return 1;\n"
+        "  /* argument errors come back as codes + message, never as exceptions or aborts */\n"
+        "  if (mip360_adamw(0, 0, 0, 0, 0, 1e-3f, 0.9f, 0.999f, 1e-8f, 0.f, 1, 0) != MIP360_ERR_ARG) return 2;\n"
+        "  if (strstr(mip360_last_error(), \"adamw\") == 0) return 3;\n"
+        "  if (mip360_set_option(99, 1) != MIP360_ERR_ARG) return 4;\n"
+        '  printf("ok %d %d\\n", mip360_partials_len(1), (int)sizeof l);\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi_demo"
+    libdir = os.path.dirname(lib_path)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lmip360_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok "), (out.returncode, out.stdout, out.stderr)
+
+
 def test_no_cpu_fallback(lib_path):
     from mipnerf360_b200 import _lib, ops
     with pytest.raises(_lib.Mip360Error):
