@@ -17,7 +17,9 @@ void set_error(const char* fmt, ...);
 enum { OPT_RAY_GROUP = 0, OPT_CTA_PAIR = 1, OPT_SHORT_K = 2, OPT_COUNT = 3 };
 bool option(int key);
 void count_launch(int n = 1);
-int sm_count();
+constexpr int MAX_DEVICES = 64;
+int current_device();  // cudaGetDevice, clamped to [0, MAX_DEVICES)
+int sm_count();        // SMs of the current device
 
 #define MIP_REQUIRE(cond, ...)                  \
   do {                                          \

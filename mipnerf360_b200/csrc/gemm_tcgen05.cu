@@ -596,11 +596,12 @@ template <int BN, int EPI, int CG, int OCC = 1>
 static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* yprev, const LinearParams& p,
                          cudaStream_t stream) {
   using Cfg = LinearCfg<BN, CG, OCC>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {};  // the attribute is per device (one process may drive several)
+  const int dev = current_device();
+  if (!configured[dev]) {
     MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   CUtensorMap ta, tb, tout, ty;
   int rc;
@@ -654,10 +655,11 @@ static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t
 template <int BN, int CG>
 static int launch_wgrad(const uint16_t* dY, const uint16_t* X, WgradParams p, cudaStream_t stream) {
   using Cfg = WgradCfg<BN, CG>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     MIP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   CUtensorMap tdy, tx;
   int rc;
