@@ -44,7 +44,8 @@ long long mip360_launch_count(void);
 void mip360_reset_launch_count(void);
 /* Runtime switch between kernel variants that compute the same function (used by the tests to compare them):
  * key 0 = 8-lanes-per-ray register kernels for N in {32,64,128} (else one warp per ray),
- * key 1 = CTA-pair (cta_group::2) GEMM tiles, key 2 = short-K two-CTAs-per-SM GEMM configuration.  All default on. */
+ * key 1 = CTA-pair (cta_group::2) GEMM tiles, key 2 = short-K two-CTAs-per-SM GEMM configuration,
+ * key 3 = packed (fp32x2 / bf16x2) arithmetic in the ReLU and trunk-Sigmoid GEMM epilogues.  All default on. */
 int mip360_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------

@@ -162,7 +162,7 @@ def reset_launch_count():
     load().mip360_reset_launch_count()
 
 
-OPT_RAY_GROUP, OPT_CTA_PAIR, OPT_SHORT_K = 0, 1, 2
+OPT_RAY_GROUP, OPT_CTA_PAIR, OPT_SHORT_K, OPT_PACKED_EPILOGUE = 0, 1, 2, 3
 
 
 def set_option(key, value):

@@ -214,6 +214,18 @@ def test_kernel_variants_agree(ops):
         _lib.set_option(_lib.OPT_SHORT_K, True)
     for k in ("fwd", "dgrad", "fwd0"):
         assert torch.equal(fast[k], slow[k]), k
+    # packed (fp32x2 / bf16x2) epilogue arithmetic against the scalar forms: the same bf16 values
+    def epilogues():
+        return dict(relu=ops.linear_fwd(x, W, bias, 1)[0], sigmoid=ops.linear_fwd(x, W, bias, 2)[0],
+                    dgrad=ops.linear_dgrad(dY, W.T.contiguous(), x, 1), relu0=ops.linear_fwd(x0, W0, bias, 1)[0])
+    packed = epilogues()
+    _lib.set_option(_lib.OPT_PACKED_EPILOGUE, False)
+    try:
+        scalar = epilogues()
+    finally:
+        _lib.set_option(_lib.OPT_PACKED_EPILOGUE, True)
+    for k in packed:
+        assert torch.equal(packed[k], scalar[k]), k
     for k in ("dW", "db"):  # split-K atomics: summation order differs
         torch.testing.assert_close(fast[k], slow[k], rtol=1e-4, atol=1e-4 * math.sqrt(M))
 
