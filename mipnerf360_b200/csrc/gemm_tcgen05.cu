@@ -185,6 +185,27 @@ __device__ __forceinline__ void bwd_relu_packed(const uint32_t (&v)[32], const u
   }
 }
 
+//   dgrad through a Sigmoid:  acc * y (1 - y) with the subtraction and both multiplications as fp32x2
+__device__ __forceinline__ void bwd_sigmoid_packed(const uint32_t (&v)[32], const uint32_t* yw, uint32_t* pk) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint32_t r0, r1;
+    asm("{\n"
+        ".reg .b64 y, one, d, a;\n"
+        "mov.b64 y, {%4, %5};\n"
+        "mov.b64 one, {%6, %6};\n"
+        "sub.rn.f32x2 d, one, y;\n"
+        "mul.rn.f32x2 d, y, d;\n"
+        "mov.b64 a, {%2, %3};\n"
+        "mul.rn.f32x2 a, a, d;\n"
+        "mov.b64 {%0, %1}, a;\n"
+        "}\n"
+        : "=r"(r0), "=r"(r1)
+        : "r"(v[2 * i]), "r"(v[2 * i + 1]), "r"(yw[i] << 16), "r"(yw[i] & 0xffff0000u), "r"(0x3f800000u));
+    pk[i] = pack_bf16x2(__uint_as_float(r0), __uint_as_float(r1));
+  }
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -371,6 +392,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           }
           if (EPI == EPI_DGRAD && p.act == ACT_RELU && p.packed_epi) {
             bwd_relu_packed(v, reinterpret_cast<const uint32_t*>(&yv[4 * h]), &packed[16 * h]);
+            continue;
+          }
+          if (EPI == EPI_DGRAD && p.act == ACT_SIGMOID && p.packed_epi) {
+            bwd_sigmoid_packed(v, reinterpret_cast<const uint32_t*>(&yv[4 * h]), &packed[16 * h]);
             continue;
           }
           float x[32];

@@ -215,9 +215,12 @@ def test_kernel_variants_agree(ops):
     for k in ("fwd", "dgrad", "fwd0"):
         assert torch.equal(fast[k], slow[k]), k
     # packed (fp32x2 / bf16x2) epilogue arithmetic against the scalar forms: the same bf16 values
+    y_sig = torch.sigmoid(x.float()).to(torch.bfloat16)
+
     def epilogues():
         return dict(relu=ops.linear_fwd(x, W, bias, 1)[0], sigmoid=ops.linear_fwd(x, W, bias, 2)[0],
-                    dgrad=ops.linear_dgrad(dY, W.T.contiguous(), x, 1), relu0=ops.linear_fwd(x0, W0, bias, 1)[0])
+                    dgrad=ops.linear_dgrad(dY, W.T.contiguous(), x, 1), relu0=ops.linear_fwd(x0, W0, bias, 1)[0],
+                    dgrad_sigmoid=ops.linear_dgrad(dY, W.T.contiguous(), y_sig, 2))
     packed = epilogues()
     _lib.set_option(_lib.OPT_PACKED_EPILOGUE, False)
     try:
