@@ -358,6 +358,33 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (EPI == EPI_FWD && !tma_out) {
+        // fp32-only output = an MLP head: n_valid <= 8 real columns in the first column tile; nothing else of the
+        // accumulator is read, no activation is evaluated on padding
+        if (n0 == 0) {
+          uint32_t v8[8];
+          tmem_ld_32x8(t_row, v8);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float* o = p.out_f32 + (size_t)row * p.n_valid;
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float bv;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(bias_smem + 4u * i));
+              const float z = __uint_as_float(v8[i]) + bv;
+              r[i] = p.act == ACT_SIGMOID ? __fdividef(1.f, 1.f + __expf(-z)) : (p.act == ACT_RELU ? fmaxf(z, 0.f) : z);
+            }
+            if (p.n_valid == 4) {
+              *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.n_valid) o[i] = r[i];
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int jj = 0; jj < BN / 64; ++jj) {
         const uint32_t box = box0 + bi * Cfg::EPI_BOX_BYTES;
