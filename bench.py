@@ -244,7 +244,7 @@ def main():
         r = run_cpu(args.cpu_sample_rays, args.steps, min(args.warmup, 1))
         sample = f"{args.cpu_sample_rays} rays of the same iteration per step (oracle port of the reference, fp32 torch CPU)"
         print(json.dumps({
-            "impl": "reference", "metric": "train rays/s", "value": r["value"], "unit": "rays/s", "n_gpus": 0,
+            "impl": "reference", "metric": "train rays/s", "value": r["value"], "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "sample": sample},
