@@ -341,12 +341,20 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     int first[E], nR[E], baseF[E], baseR[E];
 #pragma unroll
     for (int c = 0; c < E; ++c) {
-      int nf = 0, nr = 0;
-#pragma unroll
-      for (int l = 0; l < RG_LANES; ++l) {
-        nf += (endF[l] < L[c]) ? 1 : 0;
-        nr += (endR[l] <= R[c]) ? 1 : 0;
-      }
+      // whole chunks below the knot: bisection over the 8 sorted chunk ends held in registers (selects), then the
+      // last end separately since all 8 chunks can be full
+      const bool f1 = endF[3] < L[c];
+      const float fe2 = f1 ? endF[5] : endF[1];
+      const bool f2 = fe2 < L[c];
+      const float fe3 = f1 ? (f2 ? endF[6] : endF[4]) : (f2 ? endF[2] : endF[0]);
+      int nf = (f1 ? 4 : 0) + (f2 ? 2 : 0) + (fe3 < L[c] ? 1 : 0);
+      if (nf == 7 && endF[7] < L[c]) nf = 8;
+      const bool r1 = endR[3] <= R[c];
+      const float re2 = r1 ? endR[5] : endR[1];
+      const bool r2 = re2 <= R[c];
+      const float re3 = r1 ? (r2 ? endR[6] : endR[4]) : (r2 ? endR[2] : endR[0]);
+      int nr = (r1 ? 4 : 0) + (r2 ? 2 : 0) + (re3 <= R[c] ? 1 : 0);
+      if (nr == 7 && endR[7] <= R[c]) nr = 8;
       // skewed positions of the partial chunks: knot E*n + o sits at (E+1)*n + o for o < E
       baseF[c] = nf * (E + 1);
       baseR[c] = nr * (E + 1);

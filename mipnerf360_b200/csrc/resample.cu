@@ -296,9 +296,13 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
         u[c] = (u[c] + u[c]) + jit[c];  // the doubled stratum offset is the reference's (App. A5)
         u[c] = fminf(u[c], one_m_eps);
       }
-      int nfull = 0;
-#pragma unroll
-      for (int l = 0; l < RG_LANES; ++l) nfull += (chunk_end[l] <= u[c]) ? 1 : 0;
+      // number of chunk ends <= u (sorted; the last one, cdf[N] = 1 > u, never counts): a 3-step bisection over the
+      // 8 registers with selects instead of 8 compare-and-add pairs
+      const bool p1 = chunk_end[3] <= u[c];
+      const float e2 = p1 ? chunk_end[5] : chunk_end[1];
+      const bool p2 = e2 <= u[c];
+      const float e3 = p1 ? (p2 ? chunk_end[6] : chunk_end[4]) : (p2 ? chunk_end[2] : chunk_end[0]);
+      const int nfull = (p1 ? 4 : 0) + (p2 ? 2 : 0) + (e3 <= u[c] ? 1 : 0);
       // the partial chunk holds knots E*n+1 .. E*n+E, skewed position (E+1)*n + 1 + offset (contiguous up to E-1)
       cbase[c] = min(nfull, RG_LANES - 1) * (E + 1);
       cnt[c] = 0;  // nfull == 8 (u >= cdf[N] = 1) cannot happen: u <= 1 - eps
