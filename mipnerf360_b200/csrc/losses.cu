@@ -308,14 +308,12 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     float w[E];
     rg_load<E>(w_fine + ray * N + j0, w);
     // the coarse knots are fetched now, together with the fine row, so that the searches below do not start a
-    // second round trip to memory
+    // second round trip to memory.  A lane owns the knots gl + 8c (c < E); slot E is knot N (used by lane 0).
+    constexpr int S = E + 1;
     const float* tc = t_coarse + ray * K;
-    float L[E], R[E];
+    float X[S];
 #pragma unroll
-    for (int c = 0; c < E; ++c) {
-      L[c] = __ldg(tc + gl + RG_LANES * c);
-      R[c] = __ldg(tc + gl + RG_LANES * c + 1);
-    }
+    for (int c = 0; c < S; ++c) X[c] = __ldg(tc + ((c < E) ? gl + RG_LANES * c : N));
     double run = 0.0, ex[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) {
@@ -327,56 +325,53 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
     for (int i = 0; i < E; ++i) cws[rg_skew_l<E>(j0 + i)] = off + ex[i];
     if (gl == RG_LANES - 1) cws[rg_skew_l<E>(N)] = off + run;
     __syncwarp();
-    // two-level counting search:
-    //   first = #{j < N : t1_j = tf[j+1] < L}   (= first j with t1_j >= L),   nR = #{j < N : t0_j = tf[j] <= R}
-    // Level 1 (registers): end knots of the 8 lane chunks, t1 of the chunk's last interval (tf[(l+1)E]) for `first`,
-    // its t0 (tf[(l+1)E - 1]) for `nR`; whole chunks are a sum of predicates.  Level 2: log2(E) shared-memory
-    // probes inside the one partial chunk, the lane's E intervals in lock step.
-    float endF[RG_LANES], endR[RG_LANES];
+    // ONE search per coarse knot x (not two per interval): with
+    //   A(x) = #{j < N : t1_j = tf[j+1] < x}   and   B(x) = #{j < N : t0_j = tf[j] <= x}
+    // interval i = [x_i, x_{i+1}] needs first = A(x_i) and nR = B(x_{i+1}), and the two counts of one knot differ
+    // only by its ties:  B(x) = A(x) + [tf[0] < x] + #{m : tf[m] == x} - [tf[N] <= x].
+    // A(x) by the two-level counting search.  Level 1 (registers): t1 of each lane chunk's last interval
+    // (tf[(l+1)E]), bisection with selects, the last end separately since all 8 chunks can be full.  Level 2:
+    // log2(E) shared-memory probes inside the one partial chunk, the lane's knots in lock step.
+    float endF[RG_LANES];
 #pragma unroll
-    for (int l = 0; l < RG_LANES; ++l) {
-      endF[l] = tfs[rg_skew_l<E>((l + 1) * E)];
-      endR[l] = tfs[rg_skew_l<E>((l + 1) * E - 1)];
-    }
-    int first[E], nR[E], baseF[E], baseR[E];
+    for (int l = 0; l < RG_LANES; ++l) endF[l] = tfs[rg_skew_l<E>((l + 1) * E)];
+    const float tf0 = tfs[0], tfN = endF[RG_LANES - 1];
+    int first[S], baseF[S];
 #pragma unroll
-    for (int c = 0; c < E; ++c) {
-      // whole chunks below the knot: bisection over the 8 sorted chunk ends held in registers (selects), then the
-      // last end separately since all 8 chunks can be full
-      const bool f1 = endF[3] < L[c];
+    for (int c = 0; c < S; ++c) {
+      const bool f1 = endF[3] < X[c];
       const float fe2 = f1 ? endF[5] : endF[1];
-      const bool f2 = fe2 < L[c];
+      const bool f2 = fe2 < X[c];
       const float fe3 = f1 ? (f2 ? endF[6] : endF[4]) : (f2 ? endF[2] : endF[0]);
-      int nf = (f1 ? 4 : 0) + (f2 ? 2 : 0) + (fe3 < L[c] ? 1 : 0);
-      if (nf == 7 && endF[7] < L[c]) nf = 8;
-      const bool r1 = endR[3] <= R[c];
-      const float re2 = r1 ? endR[5] : endR[1];
-      const bool r2 = re2 <= R[c];
-      const float re3 = r1 ? (r2 ? endR[6] : endR[4]) : (r2 ? endR[2] : endR[0]);
-      int nr = (r1 ? 4 : 0) + (r2 ? 2 : 0) + (re3 <= R[c] ? 1 : 0);
-      if (nr == 7 && endR[7] <= R[c]) nr = 8;
-      // skewed positions of the partial chunks: knot E*n + o sits at (E+1)*n + o for o < E
-      baseF[c] = nf * (E + 1);
-      baseR[c] = nr * (E + 1);
+      int nf = (f1 ? 4 : 0) + (f2 ? 2 : 0) + (fe3 < X[c] ? 1 : 0);
+      if (nf == 7 && endF[7] < X[c]) nf = 8;
+      baseF[c] = nf * (E + 1);  // skewed position of the partial chunk: knot E*n + o sits at (E+1)*n + o for o < E
       first[c] = 0;
-      nR[c] = 0;
     }
 #pragma unroll
     for (int step = E / 2; step > 0; step >>= 1) {
 #pragma unroll
-      for (int c = 0; c < E; ++c) {
-        // (all-chunks-full cases probe past the row's knots into its padding / the next row: harmless, see below)
-        const float vf = tfs[min(baseF[c] + first[c] + step, ROW - 1)];      // t1 of interval E*nf + (first+step) - 1
-        const float vr = tfs[min(baseR[c] + nR[c] + step - 1, ROW - 1)];     // t0 of interval E*nr + (nR+step) - 1
-        if (vf < L[c]) first[c] += step;
-        if (vr <= R[c]) nR[c] += step;
+      for (int c = 0; c < S; ++c) {
+        // (the all-chunks-full case probes past the row's knots into its padding: harmless, the count is N then)
+        const float vf = tfs[min(baseF[c] + first[c] + step, ROW - 1)];  // t1 of interval E*nf + (first+step) - 1
+        if (vf < X[c]) first[c] += step;
       }
+    }
+    int cntA[S], cntB[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      const int nf = baseF[c] / (E + 1);
+      cntA[c] = nf == RG_LANES ? N : nf * E + first[c];
+      int p = cntA[c] + (tf0 < X[c] ? 1 : 0);                        // knots (0..N) strictly below x
+      while (p <= N && tfs[rg_skew_l<E>(p)] == X[c]) ++p;             // + its ties (0 or 1 except on collapsed rows)
+      cntB[c] = p - (tfN <= X[c] ? 1 : 0);
     }
 #pragma unroll
     for (int c = 0; c < E; ++c) {
-      // interval counts: f = E*nf + first, r = E*nr + nR; with every chunk full (nf or nr == 8) the count is N
-      const int nf = baseF[c] / (E + 1), nr = baseR[c] / (E + 1);
-      const int f = nf == RG_LANES ? N : nf * E + first[c], r = nr == RG_LANES ? N : nr * E + nR[c];
+      // B of knot i + 1: the next lane's knot of the same slot, or lane 0's next slot for the last lane
+      const int b_dn = __shfl_down_sync(FULL_MASK, cntB[c], 1, RG_LANES);
+      const int b_l0 = __shfl_sync(FULL_MASK, cntB[c + 1], 0, RG_LANES);
+      const int f = cntA[c], r = gl == RG_LANES - 1 ? b_l0 : b_dn;
       float v = 0.f;
       if (r - 1 >= f) v = fmaxf((float)(cws[rg_skew_l<E>(r)] - cws[rg_skew_l<E>(f)]), 0.f);
       if (active) b_out[ray * N + gl + RG_LANES * c] = v;
