@@ -52,7 +52,8 @@ def turbo_lut(n=256):
 
 
 def _colour_table(colormap):
-    """None | 'sinebow' | the sinebow function -> None (evaluated on the device); tables and listed colour maps -> [n,3]."""
+    """None | 'sinebow' | the sinebow function -> None (evaluated on the device); tables and listed colour maps ->
+    host fp32 table [n,3]."""
     if colormap is None or colormap is sinebow or (isinstance(colormap, str) and colormap == "sinebow"):
         return None
     if hasattr(colormap, "colors"):  # matplotlib ListedColormap
@@ -63,9 +64,9 @@ def _colour_table(colormap):
         raise TypeError("visualize_depth: colormap must be a colour table [n,3], a matplotlib Colormap or sinebow; "
                         "arbitrary Python callables cannot run on the device and there is no host fallback")
     table = np.asarray(colormap.cpu() if isinstance(colormap, torch.Tensor) else colormap, dtype=np.float32)
-    if table.ndim != 2 or table.shape[1] < 3:
-        raise ValueError(f"visualize_depth: colour table must be [n, >=3], got {table.shape}")
-    return torch.as_tensor(np.ascontiguousarray(table[:, :3])).cuda()
+    if table.ndim != 2 or table.shape[1] < 3 or table.shape[0] < 1:
+        raise ValueError(f"visualize_depth: colour table must be [n >= 1, >= 3], got {table.shape}")
+    return np.ascontiguousarray(table[:, :3])
 
 
 def visualize_normals(depth, acc, scaling=None, as_uint8=False):
@@ -88,6 +89,8 @@ def visualize_depth(depth, acc=None, near=None, far=None, ignore_frac=0, curve_f
     a, _ = _to_device(acc)
     table = _colour_table(colormap)  # None = sinebow, evaluated on the device
     if colormap is None and not modulus > 0:
-        table = torch.as_tensor(turbo_lut()).cuda()  # pose.py:204: turbo unless the depth is wrapped
+        table = turbo_lut()  # pose.py:204: turbo unless the depth is wrapped
+    if table is not None:
+        table = torch.as_tensor(table).cuda()
     out = ops.visualize_depth(d, a, near, far, ignore_frac, curve_fn, modulus, table, as_uint8=as_uint8)
     return _back(out, as_numpy)

@@ -52,6 +52,42 @@ def test_oracle_depth_equals_reference(tag):
     np.testing.assert_allclose(vis, Z[tag + "/vis"], rtol=0, atol=1e-6, equal_nan=True)
 
 
+def test_colour_tables_host_logic():
+    """Host side of visualize_depth: what is accepted as a colour map and what the default table looks like."""
+    from mipnerf360_b200.intern import pose as P
+    lut = P.turbo_lut()
+    assert lut.shape == (256, 3) and lut.dtype == np.float32 and lut.min() >= 0 and lut.max() <= 1
+    assert lut[230, 0] > 2 * lut[230, 2] and lut[25, 2] > 2 * lut[25, 0]          # red at the near end, blue at the far end
+    assert P._colour_table(None) is None and P._colour_table("sinebow") is None and P._colour_table(P.sinebow) is None
+    rgba = np.random.default_rng(0).uniform(size=(17, 4)).astype(np.float32)
+    for given in (rgba, rgba.tolist(), torch.as_tensor(rgba)):
+        assert np.array_equal(P._colour_table(given), rgba[:, :3])
+
+    class Listed:                       # duck-typed matplotlib ListedColormap
+        colors = rgba
+
+    class Segmented:                    # duck-typed matplotlib Colormap: integer input indexes its table
+        N = 17
+
+        def __call__(self, idx):
+            return rgba[idx]
+
+    assert np.array_equal(P._colour_table(Listed()), rgba[:, :3])
+    assert np.array_equal(P._colour_table(Segmented()), rgba[:, :3])
+    with pytest.raises(TypeError):
+        P._colour_table(lambda v: v)
+    with pytest.raises(ValueError):
+        P._colour_table(np.zeros((5, 2)))
+    # the reference's sinebow (pose.py:123-126)
+    h = np.linspace(0, 1, 11, dtype=np.float32)
+    np.testing.assert_allclose(P.sinebow(h).numpy(), V.sinebow(h), atol=1e-6)
+    with pytest.raises(TypeError):
+        P.visualize_depth(np.ones((4, 4), np.float32), None, 1.0, 2.0, curve_fn=lambda x: x)
+    if not torch.cuda.is_available():   # no device: the product path fails loudly, there is no host fallback
+        with pytest.raises(Exception):
+            P.visualize_depth(np.ones((4, 4), np.float32), None, 1.0, 2.0)
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def pose():
