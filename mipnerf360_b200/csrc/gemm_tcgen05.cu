@@ -666,18 +666,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
   }
 }
 
-// fp32 [N,K] -> bf16 [Npad,Kpad] (+ transposed [Kpad,Npad]), zero padded
+// fp32 [N,K] -> bf16 [Npad,Kpad] (+ transposed [Kpad,Npad]), zero padded.  32 x 32 tiles through shared memory so
+// that the read, the straight copy and the transposed copy are all coalesced (Npad, Kpad are multiples of 32).
 __global__ void __launch_bounds__(256)
 cast_weight_kernel(const float* __restrict__ W, int N, int K, int Npad, int Kpad, uint16_t* __restrict__ Wb,
                    uint16_t* __restrict__ Wt) {
-  const long long total = (long long)Npad * Kpad;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(e / Kpad), k = (int)(e - (long long)n * Kpad);
+  __shared__ uint16_t tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 4 rows each
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
     const float v = (n < N && k < K) ? W[(long long)n * K + k] : 0.f;
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
     const uint16_t bits = *reinterpret_cast<const uint16_t*>(&b);
-    if (Wb) Wb[e] = bits;
-    if (Wt) Wt[(long long)k * Npad + n] = bits;
+    if (Wb) Wb[(long long)n * Kpad + k] = bits;
+    tile[r][tx] = bits;
+  }
+  __syncthreads();
+  if (Wt) {
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) Wt[(long long)(k0 + r) * Npad + n0 + tx] = tile[tx][r];
   }
 }
 
@@ -884,10 +893,8 @@ int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_
                        mip360_stream_t stream) {
   MIP_REQUIRE(W && (Wb || Wt), "cast_weight: null pointer");
   MIP_REQUIRE(N > 0 && K > 0 && Npad >= N && Kpad >= K, "cast_weight: bad shape");
-  const long long total = (long long)Npad * Kpad;
-  int grid = (int)((total + 255) / 256);
-  if (grid > sm_count() * 8) grid = sm_count() * 8;
-  cast_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, N, K, Npad, Kpad, Wb, Wt);
+  MIP_REQUIRE(Npad % 32 == 0 && Kpad % 32 == 0, "cast_weight: padded shape [%d, %d] must be multiples of 32", Npad, Kpad);
+  cast_weight_kernel<<<dim3(Kpad / 32, Npad / 32), 256, 0, (cudaStream_t)stream>>>(W, N, K, Npad, Kpad, Wb, Wt);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
