@@ -177,8 +177,13 @@ def test_kernel_variants_agree(ops):
         w_d = w.clone().requires_grad_(True)
         ld = ops.distortion_loss(t / t[:, -1:], w_d)
         ld.backward()
+        z_d = (w * 30 - 1).clone().requires_grad_(True)  # weights-only compositing on raw proposal logits
+        wp = ops.density_to_weight(t, z_d, dirs, raw_logits=True, density_bias=-1.0)
+        (wp * gw).sum().backward()
+        nsq = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, dirs, b, N).float()
         return dict(resample=ops.resample(t, w, True, 0.01, jitter=jit), comp=c, dist=d, acc=a, weights=ww,
-                    g_raw=raw_d.grad, bounds=ops.bounds_per_ray(t, w, t2), loss_dist=ld, g_dist=w_d.grad)
+                    g_raw=raw_d.grad, bounds=ops.bounds_per_ray(t, w, t2), loss_dist=ld, g_dist=w_d.grad,
+                    prop_weights=wp, g_logits=z_d.grad, norm_sq=nsq.reshape(1))
 
     fast = per_ray()
     _lib.set_option(_lib.OPT_RAY_GROUP, False)
