@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — train rays/s of one reference training iteration (train.py:51-82) on synthetic rays.
+"""bench.py — train rays/s of one reference training iteration (train.py:51-82) on synthetic rays, plus render rays/s.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference ...                     # the reference algorithm on the host cores
 
-Workload (BASELINE.json configs[1]): 16384 rays per GPU per iteration, 64 samples per ray, default config.py
+Workload (BASELINE.json configs[1]): ONE 16384-ray batch per iteration, 64 samples per ray, default config.py
 architecture (prop 58-256x4-1, nerf 58-1024x8-{1,3}), random-init weights, randomized sampling, bf16 MLP.
 One "step" = 2 proposal sub-steps + 1 NeRF sub-step, each with its AdamW update, exactly the reference's
-iteration.  N > 1: one process per GPU (torchrun), every rank holds its own 16384-ray shard (weak scaling),
-gradients and the reference's batch-coupled scalars are all-reduced over NCCL.
+iteration.  N > 1: one process per GPU (torchrun); the 16384-ray batch is SHARDED over the ranks (16384/N rays each,
+"scaling": "strong", as configs[1] / SURVEY §8e specify), gradients are all-reduced per layer bucket over NCCL and the
+reference's batch-coupled scalars are all-reduced too; the sharded step is checked against the unsharded one before
+timing.  The weak-scaling number (16384 rays per GPU) is reported next to it under "weak_scaling".
+
+The same line carries "render": BASELINE.json configs[2] and [3] (1008x756 LLFF-shaped NDC frame, 4946x3286
+garden-shaped unbounded frame) rendered through render.render_frame — device ray generation, chunk loop, to8b,
+image gather at N > 1 and the device->host copy all inside the timed region — at chunks 65536 and 4096.
 
 Prints ONE JSON line (see the contract in the task statement); timing is CUDA events on the launching stream,
 max over ranks; inputs are far larger than L2 (2 GB activations per layer), so no explicit L2 flush is needed.
@@ -43,20 +49,8 @@ def peaks():
 
 def synth_rays(B, seed, device=None, pin=False):
     """SURVEY §8d 'Generic' synthetic rays: origins, directions ~ N(0,I), radii 1e-3, near 0.1, far 10."""
-    from mipnerf360_b200.intern.ray import Rays
-    g = torch.Generator().manual_seed(seed)
-    o = torch.randn(B, 3, generator=g)
-    d = torch.randn(B, 3, generator=g)
-    rays = Rays(o, d, d / d.norm(dim=-1, keepdim=True), torch.full((B, 1), 1e-3), torch.full((B, 1), 0.1),
-                torch.full((B, 1), 10.0))
-    pixels = torch.rand(B, 3, generator=g)
-    if pin:
-        rays = Rays(*[r.pin_memory() for r in rays])
-        pixels = pixels.pin_memory()
-    if device is not None:
-        rays = Rays(*[r.to(device) for r in rays])
-        pixels = pixels.to(device)
-    return rays, pixels
+    from mipnerf360_b200.synthetic import generic_rays
+    return generic_rays(B, seed, device=device, pin=pin)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -68,9 +62,8 @@ def cpu_iteration(O, params, opt, rays, pixels, N):
     names_n = [k for k in params if k.startswith("nerf_net")]
     for _ in range(2):
         t_hat, w_hat = O.prop_forward(params, rays, N, True)
-        with torch.no_grad():
-            out = O.nerf_forward(params, rays, t_hat, w_hat, True)
-        lp = O.Loss_prop(out[3], out[4], t_hat, w_hat)
+        out = O.nerf_forward(params, rays, t_hat, w_hat, True)  # the reference builds this graph, then detaches (train.py:55-57)
+        lp = O.Loss_prop(out[3].detach(), out[4].detach(), t_hat, w_hat)
         opt.zero_grad()
         for k, g in zip(names_p, torch.autograd.grad(lp, [params[k] for k in names_p])):
             params[k].grad = g
@@ -88,6 +81,7 @@ def cpu_iteration(O, params, opt, rays, pixels, N):
 
 
 def run_cpu(sample_rays, steps, warmup):
+    """The reference's algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample of the workload."""
     from oracle import mip360_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -220,37 +214,108 @@ def summarise_profile(prof, steps, pk):
     return rows, total / steps
 
 
+GLOBAL_RAYS = 16384
+
+
+def workload_config(n_gpus, global_rays, scaling):
+    """The `config` object of the JSON line: identical in both arms (the reference arm runs a bounded sample of it)."""
+    per = global_rays // n_gpus if scaling == "strong" else global_rays
+    return {"workload": f"train iteration (2 prop + 1 nerf sub-steps, AdamW) on one {global_rays if scaling == 'strong' else per * n_gpus}-ray "
+                        f"batch x {N_SAMPLES} samples, default config.py widths, randomized, bf16 MLP (BASELINE configs[1])",
+            "global_rays_per_step": global_rays if scaling == "strong" else per * n_gpus, "rays_per_gpu": per,
+            "parallelism": f"ray-sharded dp{n_gpus}",
+            "l2": "activations per layer exceed L2 (>= 268 MB per layer at 2048 rays/GPU); no flush needed"}
+
+
+def time_train(trainer, rays, pixels, steps, warmup, barrier, dev, world):
+    """W warm-up steps, then EXACTLY K steps between CUDA events with a barrier + synchronize on both sides; max over ranks."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        trainer.step(rays, pixels)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        trainer.step(rays, pixels)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / steps
+
+
+def bench_render(model, dev, world, barrier, pk, chunk_sizes, cases):
+    """configs[2]/[3]: whole frames through render.render_frame.  Host wall clock between barriers (the call ends with the
+    device->host copy of the frame), max over ranks."""
+    import torch.distributed as dist
+    from mipnerf360_b200.render import render_frame
+    rows = []
+    flop_per_ray = N_SAMPLES * (PROP_FLOP_PER_SAMPLE + NERF_FLOP_PER_SAMPLE)
+    for case in cases:
+        h, w = case["height"], case["width"]
+        for chunks in chunk_sizes:
+            warm_h = max(3, min(h, (8 * chunks * world + w - 1) // w))  # a few chunks per rank
+            render_frame(model, case["c2w"], warm_h, w, case["focal"], case["near"], case["far"], case["ndc"], chunks)
+            barrier()
+            t0 = time.perf_counter()
+            rgb8, d, a = render_frame(model, case["c2w"], h, w, case["focal"], case["near"], case["far"], case["ndc"], chunks)
+            barrier()
+            sec = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+            sec = float(sec)
+            n = h * w
+            rows.append(dict(case=case["name"], rays=n, chunks=chunks, n_gpus=world, seconds=sec, rays_per_s=n / sec,
+                             tensor_frac=n * flop_per_ray / sec / 1e12 / (pk["tf_sustained"] * world),
+                             d2h_bytes=int(rgb8.nbytes + d.nbytes + a.nbytes), finite=bool((a == a).all()),
+                             mean_acc=float(a.mean())))
+            del rgb8, d, a
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=16384, help="rays per GPU per iteration")
+    ap.add_argument("--rays", type=int, default=GLOBAL_RAYS, help="rays of the (global) batch per iteration")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: shard the --rays batch over the ranks (strong, configs[1]) or give every rank --rays rays")
     ap.add_argument("--cpu-sample-rays", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the additional weak-scaling measurement")
+    ap.add_argument("--render-chunks", default="65536,4096")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel roofline table (JSON) here")
     args = ap.parse_args()
+
+    if args.impl == "b200" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: start one process per GPU ourselves
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29541"),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"train iteration (2 prop + 1 nerf sub-steps, AdamW), {args.rays} rays/GPU x {N_SAMPLES} samples, " \
-               "default config.py widths, randomized, bf16 MLP"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_cpu(args.cpu_sample_rays, args.steps, min(args.warmup, 1))
-        sample = f"{args.cpu_sample_rays} rays of the same iteration per step (oracle port of the reference, fp32 torch CPU)"
+        warm = args.warmup
+        r = run_cpu(args.cpu_sample_rays, args.steps, warm)
+        sample = (f"{args.cpu_sample_rays} rays of the same iteration per step; oracle port of the reference (fp32 torch CPU, "
+                  f"{r['threads']} threads): /root/reference is Python and absent on the GPU box")
         print(json.dumps({
             "impl": "reference", "metric": "train rays/s", "value": r["value"], "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
+            "steps": args.steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus, args.rays, args.scaling),
             "cpu_baseline": {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        }), flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
@@ -258,8 +323,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # NCCL_DEBUG is left as the caller set it
     from mipnerf360_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):  # fresh checkout on a box with nvcc: build once (rank 0), never fall back
         if rank == 0:
@@ -268,21 +332,45 @@ def main():
         if world > 1:
             dist.barrier()
     from mipnerf360_b200.model import mipNeRF360
-    from mipnerf360_b200.train import Trainer
-
-    torch.manual_seed(0)
-    model = mipNeRF360(randomized=True, num_samples=N_SAMPLES, device=dev)  # identical init on every rank (seed 0)
-    trainer = Trainer(model)
-    rays, pixels = synth_rays(args.rays, 1000 + rank, device=dev)
-    torch.manual_seed(1234 + rank)  # sampling draws differ per rank
+    from mipnerf360_b200.synthetic import garden_case, llff_case
+    from mipnerf360_b200.train import Trainer, check_sharded_equals_unsharded
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    warmup = max(args.warmup, 3)
+    assert args.rays % world == 0, "--rays must be divisible by the number of GPUs"
+    rays_per_gpu = args.rays // world if args.scaling == "strong" else args.rays
+
+    # data-parallel correctness gate: the sharded step must equal the unsharded one (losses, gradients)
+    dp_check = None
+    if world > 1:
+        dp_check = check_sharded_equals_unsharded(dev, rays_per_rank=max(256, 2048 // world))
+        bad = {k: v for k, v in dp_check.items() if k != "world" and not v < 5e-3}
+        assert not bad, f"sharded step differs from the unsharded step: {dp_check}"
+        torch.cuda.empty_cache()
+
+    torch.manual_seed(0)
+    model = mipNeRF360(randomized=True, num_samples=N_SAMPLES, device=dev)  # identical init on every rank (seed 0)
+    trainer = Trainer(model)
+    # the global batch is drawn once (seed 1000) and sharded; weak scaling gives rank r the batch of seed 1000 + r
+    if args.scaling == "strong":
+        g_rays, g_pixels = synth_rays(args.rays, 1000)
+        sl = slice(rank * rays_per_gpu, (rank + 1) * rays_per_gpu)
+        from mipnerf360_b200.intern.ray import Rays
+        rays = Rays(*[r[sl].contiguous().to(dev) for r in g_rays])
+        pixels = g_pixels[sl].contiguous().to(dev)
+        rays_h = Rays(*[r[sl].contiguous().pin_memory() for r in g_rays])
+        pixels_h = g_pixels[sl].contiguous().pin_memory()
+    else:
+        rays, pixels = synth_rays(rays_per_gpu, 1000 + rank, device=dev)
+        rays_h, pixels_h = synth_rays(rays_per_gpu, 1000 + rank, pin=True)
+    torch.manual_seed(1234 + rank)  # sampling draws differ per rank
+
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         trainer.step(rays, pixels)
     barrier()
     # timed region: EXACTLY K steps, CUDA events on the launching stream, barrier + synchronize on both sides
@@ -302,7 +390,8 @@ def main():
     ms_step = float(ms) / args.steps
     clk = clocks.stop(t_begin, t_end) if clocks else None
     # the same K steps again with every kernel launch bracketed by CUDA events (per-kernel durations for the
-    # roofline; ~300 extra event records per step, so this pass is kept out of `value`)
+    # roofline; ~300 extra event records per step and one C call per GEMM instead of one per MLP, so this pass
+    # is kept out of `value`)
     _lib.PROFILE = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -314,7 +403,6 @@ def main():
     ms_step_instrumented = p0.elapsed_time(p1) / args.steps
 
     # end to end through the public API: pinned host rays/pixels in, losses out, every step
-    rays_h, pixels_h = synth_rays(args.rays, 1000 + rank, pin=True)
     for _ in range(2):
         trainer.step_host(rays_h, pixels_h)
     barrier()
@@ -327,8 +415,27 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     h2d = sum(r.numel() * 4 for r in rays_h) + pixels_h.numel() * 4
 
+    # N > 1: the weak-scaling figure (every rank a full 16384-ray batch) next to the strong-scaling headline
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        w_rays, w_pixels = synth_rays(args.rays, 1000 + rank, device=dev)
+        w_ms = time_train(trainer, w_rays, w_pixels, args.steps, 2, barrier, dev, world)
+        weak = {"value": args.rays * world / (w_ms * 1e-3), "unit": "rays/s", "ms_per_step": w_ms, "rays_per_gpu": args.rays,
+                "global_rays_per_step": args.rays * world}
+        del w_rays, w_pixels
+
+    pk = peaks()
+    render_rows = None
+    if not args.no_render:
+        del trainer
+        torch.cuda.empty_cache()
+        model.eval()
+        for net in (model, model.prop_net, model.nerf_net):
+            net.randomized = False  # deterministic frames (the reference's eval() leaves the flags on, App. A7)
+        chunk_sizes = [int(c) for c in args.render_chunks.split(",") if c]
+        render_rows = bench_render(model, dev, world, barrier, pk, chunk_sizes, [llff_case(), garden_case()])
+
     if rank == 0:
-        pk = peaks()
         rows, kernel_ms = summarise_profile(prof, args.steps, pk)
         if args.kernel_table:
             json.dump(dict(ms_per_step=ms_step_instrumented, kernel_ms_per_step=kernel_ms, kernels=rows), open(args.kernel_table, "w"),
@@ -341,29 +448,37 @@ def main():
             traffic = json.load(open(tpath)).get(f'{top["kernel"]}{tuple(top["args"][:3])}')
         roof = dict(bound=top["bound"], achieved=top["achieved"], peak=top["peak"], unit=top["unit"], frac=top["frac"],
                     traffic=traffic, kernel=f'{top["kernel"]}{tuple(top["args"])}', share_of_step=top["share"],
-                    peak_source=pk["src"] + " (sustained bf16)" if top["bound"] == "tensor" else pk["src"])
-        total_rays = args.rays * world
+                    peak_source=pk["src"] + " (sustained bf16)" if top["bound"] == "tensor" else pk["src"],
+                    source="per-launch CUDA events of a second, instrumented pass over the same K steps (one C call per GEMM "
+                           "instead of one per MLP: same kernels, same launch order; ms_per_step_with_kernel_events)")
+        total_rays = rays_per_gpu * world
+        flop_step = ITER_FLOP_PER_SAMPLE * N_SAMPLES * total_rays
         out = {
             "metric": "train rays/s", "value": total_rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "global_rays_per_step": total_rays, "parallelism": f"ray-sharded dp{world}",
-                       "l2": "per-layer activations (2.1 GB) exceed L2; no flush needed"},
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world, args.rays, args.scaling),
             "clocks": clk,
             "e2e": {"value": total_rays / float(e2e_s), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 12},
             "gpu_launches": launches,
             "roofline": roof,
             "ms_per_step_with_kernel_events": ms_step_instrumented,
-            "step_tflops": ITER_FLOP_PER_SAMPLE * N_SAMPLES * args.rays / (ms_step * 1e-3) / 1e12,
-            "step_tensor_frac": ITER_FLOP_PER_SAMPLE * N_SAMPLES * args.rays / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"],
+            "step_tflops": flop_step / (ms_step * 1e-3) / 1e12,
+            "step_tensor_frac": flop_step / (ms_step * 1e-3) / 1e12 / (pk["tf_sustained"] * world),
         }
+        if weak is not None:
+            out["weak_scaling"] = weak
+        if dp_check is not None:
+            out["dp_check"] = dp_check
+        if render_rows is not None:
+            out["render"] = render_rows
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu(args.cpu_sample_rays, 2, 1)
             out["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
                                    "sample": f"{args.cpu_sample_rays} rays of the same iteration, 2 timed steps, "
                                              f"oracle port of the reference (fp32 torch CPU, {r['threads']} threads)"}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

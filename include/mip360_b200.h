@@ -127,10 +127,12 @@ int mip360_resample(const float* t_vals, const float* weights, const float* u_ba
  *     density = softplus(raw0 + density_bias), rgb = raw123*(1+2*rgb_padding) - rgb_padding.
  *   weights-only variant (density_to_weight): density_mode 0 = density given, 1 = raw logits,
  *     density = softplus(raw + density_bias) (model.py:92).
- *   Backward: g_rgb [B,3], g_acc [B], g_w [B,N] (any may be NULL) -> gradient w.r.t. rgb/density
+ *   Backward: g_rgb [B,3], g_acc [B], g_dist [B], g_w [B,N] (any may be NULL) -> gradient w.r.t. rgb/density
  *     (head_mode 0: g_rgb_in [B,N,3], g_density [B,N]) or the head outputs (head_mode 1: g_raw
  *     [B,N,4] = dL/d raw).  density_to_weight: g_density = dL/d density (mode 0) or dL/d raw logit
- *     (mode 1).  distance carries no gradient.
+ *     (mode 1).  distance is differentiable w.r.t. density (through the weights, inside its clamp
+ *     range, like torch.clamp / nan_to_num); t_vals and dirs carry no gradient (they never do in the reference:
+ *     resampling runs under no_grad, ray.py:136).
  *   mip360_head_grad_pack: fp32 head-output gradient [M,n_valid] -> bf16 rows of 64 (zero padded) that
  *     feed the head dgrad/wgrad GEMMs; act 2 folds the Sigmoid derivative y(1-y) of the saved head
  *     output y (model.py:150-158), act 0 copies.
@@ -140,8 +142,8 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
                          float* comp_rgb, float* distance, float* acc, float* weights, mip360_stream_t stream);
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
-                         const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in,
-                         float* g_density, float* g_raw, mip360_stream_t stream);
+                         const float* g_rgb, const float* g_acc, const float* g_dist, const float* g_w,
+                         float* g_rgb_in, float* g_density, float* g_raw, mip360_stream_t stream);
 int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, float* weights, mip360_stream_t stream);
 int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
@@ -240,6 +242,13 @@ int mip360_sm_count(void);
 int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal, float near, float far,
                          int ndc, float ndc_near, float* origins, float* directions, float* viewdirs, float* radii,
                          float* near_out, float* far_out, mip360_stream_t stream);
+/* The same for the slab [ray_begin, ray_begin + ray_count) of the flattened ray index only (outputs hold ray_count
+ * rays): a render chunk loop (model.py:262-264) or a rank of a ray-partitioned render generates exactly the rays it
+ * is about to consume, so a frame's rays are never materialised or uploaded. */
+int mip360_generate_rays_range(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal, float near,
+                               float far, int ndc, float ndc_near, long long ray_begin, long long ray_count,
+                               float* origins, float* directions, float* viewdirs, float* radii, float* near_out,
+                               float* far_out, mip360_stream_t stream);
 
 /* intern/utils.py:17-21 (to8b, used by model.render_image, model.py:270): uint8 = 255 * clip(nan_to_num(x), 0, 1),
  * truncated like NumPy's astype(uint8); n elements (the image leaves the device as 3 B/pixel). */

@@ -39,7 +39,7 @@ SIGNATURES = {
     "mip360_resample_invert": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "mip360_resample": [P, P, P, P, c_int, c_int, c_float, c_int, P, P],
     "mip360_composite_fwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P],
-    "mip360_composite_bwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P],
+    "mip360_composite_bwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P],
     "mip360_density_to_weight_fwd": [P, P, P, c_int, c_int, c_int, c_float, P, P],
     "mip360_density_to_weight_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_head_grad_pack": [P, P, c_longlong, c_int, c_int, P, P],
@@ -59,6 +59,8 @@ SIGNATURES = {
     "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
+    "mip360_generate_rays_range": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_longlong,
+                                   c_longlong, P, P, P, P, P, P, P],
     "mip360_to8b": [P, c_longlong, P, P],
     "mip360_vis_partials_len": [],
     "mip360_vis_work_len": [],

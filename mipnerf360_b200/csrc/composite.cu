@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(CP_WARPS * 32)
 composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                      const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
                      int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
-                     const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
-                     float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw) {
+                     const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_dist,
+                     const float* __restrict__ g_w, float* __restrict__ g_rgb_in, float* __restrict__ g_density,
+                     float* __restrict__ g_raw) {
   __shared__ CompositeSmem sm[CP_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CompositeSmem& s = sm[warp];
@@ -153,15 +154,31 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
     }
     const float dx = dirs[b * 3], dy = dirs[b * 3 + 1], dz = dirs[b * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
-    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f, gd = 0.f;
     if (!weights_only) {
       if (g_rgb) { gr = g_rgb[b * 3]; gg = g_rgb[b * 3 + 1]; gb = g_rgb[b * 3 + 2]; }
       if (g_acc) ga = g_acc[b];
+      if (g_dist) gd = g_dist[b];
       if (white_bkgd) ga -= (gr + gg + gb);
     }
     __syncwarp();
     RayScan r;
     ray_weights(s, N, C, j0, dnorm, lane, r);
+    // distance = clamp(nan_to_num(sum w t_mid / acc), t_0, t_N): d/dw_j = (t_mid_j - distance)/acc where the
+    // quotient is finite and inside the clamp range (torch.clamp passes the gradient on the closed range)
+    float gd_scale = 0.f, dist_raw = 0.f;
+    if (g_dist) {
+      float a = 0.f, wt = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP_MAXC; ++c) {
+        const int j = j0 + c;
+        if (c < C && j < N) { a += r.w[c]; wt += r.w[c] * (0.5f * (s.t[j] + s.t[j + 1])); }
+      }
+      a = warp_sum(a); wt = warp_sum(wt);
+      dist_raw = wt / a;
+      const bool pass = !isnan(dist_raw) && !isinf(dist_raw) && dist_raw >= s.t[0] && dist_raw <= s.t[N];
+      gd_scale = pass ? gd / a : 0.f;
+    }
     float G[CP_MAXC], run = 0.f, excl_rev[CP_MAXC];
     // suffix sums of G_k w_k: walk the lane's chunk backwards
 #pragma unroll
@@ -171,6 +188,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
       if (c < C && j < N) {
         G[c] = (g_w ? s.gw[j] : 0.f) + ga;
         if (!weights_only) G[c] += gr * s.rgb[j * 3] + gg * s.rgb[j * 3 + 1] + gb * s.rgb[j * 3 + 2];
+        if (g_dist) G[c] += gd_scale * (0.5f * (s.t[j] + s.t[j + 1]) - dist_raw);
       }
       excl_rev[c] = run;
       run += G[c] * r.w[c];
@@ -334,8 +352,9 @@ __global__ void __launch_bounds__(RG_THREADS)
 composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                         const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
                         int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
-                        const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_w,
-                        float* __restrict__ g_rgb_in, float* __restrict__ g_density, float* __restrict__ g_raw) {
+                        const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_dist,
+                        const float* __restrict__ g_w, float* __restrict__ g_rgb_in, float* __restrict__ g_density,
+                        float* __restrict__ g_raw) {
   constexpr int N = E * RG_LANES;
   constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
@@ -346,10 +365,11 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
     rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
-    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+    float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f, gd = 0.f;
     if (!weights_only) {
       if (g_rgb) { gr = __ldg(g_rgb + ray * 3); gg = __ldg(g_rgb + ray * 3 + 1); gb = __ldg(g_rgb + ray * 3 + 2); }
       if (g_acc) ga = __ldg(g_acc + ray);
+      if (g_dist) gd = __ldg(g_dist + ray);
     }
     float G[E];
     if (g_w) {
@@ -361,11 +381,25 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     // all loads are in flight; arithmetic starts here
     rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
     if (!weights_only && white_bkgd) ga -= (gr + gg + gb);
+    // gradient through distance (see composite_bwd_kernel)
+    float gd_scale = 0.f, dist_raw = 0.f;
+    if (!weights_only && g_dist) {
+      float a = 0.f, wt = 0.f;
+#pragma unroll
+      for (int i = 0; i < E; ++i) { a += r.w[i]; wt += r.w[i] * (0.5f * (r.t[i] + r.t[i + 1])); }
+      a = rg_sum(a); wt = rg_sum(wt);
+      const float t_first = __shfl_sync(FULL_MASK, r.t[0], 0, RG_LANES);
+      const float t_last = __shfl_sync(FULL_MASK, r.t[E], RG_LANES - 1, RG_LANES);
+      dist_raw = wt / a;
+      const bool pass = !isnan(dist_raw) && !isinf(dist_raw) && dist_raw >= t_first && dist_raw <= t_last;
+      gd_scale = pass ? gd / a : 0.f;
+    }
     float run = 0.f, excl_rev[E];
 #pragma unroll
     for (int i = E - 1; i >= 0; --i) {
       G[i] += ga;
       if (!weights_only) G[i] += gr * r.c[i][0] + gg * r.c[i][1] + gb * r.c[i][2];
+      if (!weights_only && g_dist) G[i] += gd_scale * (0.5f * (r.t[i] + r.t[i + 1]) - dist_raw);
       excl_rev[i] = run;
       run += G[i] * r.w[i];
     }
@@ -504,19 +538,19 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
 
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
-                         const float* g_rgb, const float* g_acc, const float* g_w, float* g_rgb_in, float* g_density,
-                         float* g_raw, mip360_stream_t stream) {
+                         const float* g_rgb, const float* g_acc, const float* g_dist, const float* g_w, float* g_rgb_in,
+                         float* g_density, float* g_raw, mip360_stream_t stream) {
   MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs), "composite_bwd: null pointer");
   MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_bwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_bwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
-                         rgb_padding, white_bkgd, g_rgb, g_acc, g_w, g_rgb_in, g_density, g_raw);
+                         rgb_padding, white_bkgd, g_rgb, g_acc, g_dist, g_w, g_rgb_in, g_density, g_raw);
   else
     composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
-        g_w, g_rgb_in, g_density, g_raw);
+        g_dist, g_w, g_rgb_in, g_density, g_raw);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -545,12 +579,12 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_bwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
-                         density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, g_w, (float*)nullptr,
-                         g_density, (float*)nullptr);
+                         density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, g_w,
+                         (float*)nullptr, g_density, (float*)nullptr);
   else
     composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, g_w, nullptr,
-        g_density, nullptr);
+        nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr, g_w,
+        nullptr, g_density, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -13,6 +13,7 @@ struct RayGenParams {
   float focal, near, far;
   int ndc;
   float ndc_near;
+  long long ray_begin, ray_count;  // the slab [ray_begin, ray_begin + ray_count) of the flattened ray index
 };
 
 __device__ __forceinline__ void pinhole_dir(const float* R, int x, int y, int W, int H, float focal, float d[3]) {
@@ -51,11 +52,11 @@ __global__ void __launch_bounds__(256)
 raygen_kernel(const RayGenParams p, float* __restrict__ origins, float* __restrict__ directions,
               float* __restrict__ viewdirs, float* __restrict__ radii, float* __restrict__ near_out,
               float* __restrict__ far_out) {
-  const long long total = (long long)p.n_img * p.H * p.W;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int x = (int)(e % p.W);
-  const long long r = e / p.W;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // output slot
+  if (e >= p.ray_count) return;
+  const long long ray = p.ray_begin + e;
+  const int x = (int)(ray % p.W);
+  const long long r = ray / p.W;
   const int y = (int)(r % p.H), img = (int)(r / p.H);
   const float* R = p.c2w + (long long)img * p.c2w_rows * 4;
   const float cam_o[3] = {R[3], R[7], R[11]};
@@ -141,17 +142,28 @@ extern "C" int mip360_to8b(const float* x, long long n, uint8_t* out, mip360_str
   return MIP360_OK;
 }
 
+extern "C" int mip360_generate_rays_range(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal,
+                                          float near, float far, int ndc, float ndc_near, long long ray_begin,
+                                          long long ray_count, float* origins, float* directions, float* viewdirs,
+                                          float* radii, float* near_out, float* far_out, mip360_stream_t stream) {
+  MIP_REQUIRE(c2w_rows >= 3 && n_img >= 0 && H >= 3 && W >= 3, "generate_rays: bad sizes (need H, W >= 3)");
+  const long long total = (long long)n_img * H * W;
+  MIP_REQUIRE(ray_begin >= 0 && ray_count >= 0 && ray_begin + ray_count <= total,
+              "generate_rays: slab [%lld, %lld) outside the %lld rays of the frame set", ray_begin, ray_begin + ray_count, total);
+  if (ray_count == 0) return MIP360_OK;
+  MIP_REQUIRE(c2w && origins && directions && viewdirs && radii && near_out && far_out, "generate_rays: null pointer");
+  RayGenParams p{c2w, c2w_rows, n_img, H, W, focal, near, far, ndc, ndc_near, ray_begin, ray_count};
+  raygen_kernel<<<(int)((ray_count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, origins, directions, viewdirs, radii,
+                                                                                 near_out, far_out);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
 extern "C" int mip360_generate_rays(const float* c2w, int c2w_rows, int n_img, int H, int W, float focal, float near,
                                     float far, int ndc, float ndc_near, float* origins, float* directions,
                                     float* viewdirs, float* radii, float* near_out, float* far_out,
                                     mip360_stream_t stream) {
-  MIP_REQUIRE(c2w && origins && directions && viewdirs && radii && near_out && far_out, "generate_rays: null pointer");
-  MIP_REQUIRE(c2w_rows >= 3 && n_img >= 0 && H >= 3 && W >= 3, "generate_rays: bad sizes (need H, W >= 3)");
-  const long long total = (long long)n_img * H * W;
-  if (total == 0) return MIP360_OK;
-  RayGenParams p{c2w, c2w_rows, n_img, H, W, focal, near, far, ndc, ndc_near};
-  raygen_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, origins, directions, viewdirs, radii,
-                                                                             near_out, far_out);
-  MIP_LAUNCH_CHECK();
-  return MIP360_OK;
+  const long long total = (n_img >= 0 && H >= 0 && W >= 0) ? (long long)n_img * H * W : 0;
+  return mip360_generate_rays_range(c2w, c2w_rows, n_img, H, W, focal, near, far, ndc, ndc_near, 0, total, origins,
+                                    directions, viewdirs, radii, near_out, far_out, stream);
 }

@@ -37,6 +37,14 @@ class PackedMLP:
         self.n_valid = sum(h.out_features for h in heads)
         self._key = None
         self._packed = None
+        # Opt-in (set by train.FlatAdamW): backward adds every dW/db straight into the preallocated .grad tensors
+        # and returns None to autograd.  Off by default, so torch.autograd.grad(), tensor hooks and DDP see the
+        # gradients of every layer through autograd.
+        self.direct_grad = False
+        # With direct_grad: called as grad_hook(l) right after the gradients of trunk layer l (and, for
+        # l == len(trunk) - 1, of the heads) are complete — the data-parallel trainer all-reduces that bucket
+        # on a side stream while the remaining dgrad/wgrad GEMMs run (train.py:61-64,79-82 across ranks).
+        self.grad_hook = None
 
     def invalidate(self):
         """Force a re-cast of the bf16 operands (for optimisers that update the weights behind autograd's back)."""
@@ -89,9 +97,10 @@ class _MLPFunction(torch.autograd.Function):
     The input needs no gradient (nothing upstream of the encodings is trainable)."""
 
     @staticmethod
-    def forward(ctx, x, mlp, *params):
+    def forward(ctx, x, mlp, need_grad, *params):
+        # need_grad comes from mlp_apply: ctx.needs_input_grad does not see torch.no_grad(), so reading it here
+        # would keep every activation buffer alive on inference passes
         layers, (Wh, Wht, bh) = mlp.packed()
-        need_grad = any(ctx.needs_input_grad[2:])  # grad mode is off inside forward(); autograd tells us here
         acts = [a for _, a in mlp.trunk]
         M, L = x.shape[0], len(layers)
         if _lib.PROFILE is not None:
@@ -112,6 +121,7 @@ class _MLPFunction(torch.autograd.Function):
                 wmax = max(Wb.shape[0] for Wb, _, _ in layers)
                 bufs = [torch.empty((M, wmax), device=x.device, dtype=torch.bfloat16) for _ in range(2)]
             out = torch.empty((M, mlp.n_valid), device=x.device, dtype=torch.float32)
+            mlp.last_n_act_bufs = len(bufs)  # 2 = inference ping-pong, n_trunk = saved for backward
             ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
             _lib.call("mip360_mlp_fwd", x.data_ptr(), M, trunk_arr, L, ctypes.byref(head), mlp.n_valid, ptrs, len(bufs),
                       out.data_ptr())
@@ -130,13 +140,15 @@ class _MLPFunction(torch.autograd.Function):
         L = len(layers)
         M = saved[0].shape[0]
         dev = saved[0].device
+        direct = mlp.direct_grad and all(p.grad is not None for p in mlp.params())
 
         def grad_targets(lin, n_pad, k_pad):
-            """(dW, db, direct): the layer's preallocated .grad buffers when they can be accumulated into directly
-            (unpadded layer, e.g. views of train.FlatAdamW's flat buffer), else fresh zero-initialised scratch."""
+            """(dW, db, in_place): with direct_grad, the layer's preallocated .grad buffers when the GEMM can
+            accumulate into them as they are (unpadded layer, e.g. views of train.FlatAdamW's flat buffer);
+            otherwise fresh zero-initialised padded scratch."""
             gw, gb = lin.weight.grad, lin.bias.grad
-            if (gw is not None and gb is not None and gw.is_contiguous() and gb.is_contiguous()
-                    and gw.dtype == torch.float32 and tuple(gw.shape) == (n_pad, k_pad)):
+            if (direct and gw.is_contiguous() and gb.is_contiguous() and gw.dtype == torch.float32
+                    and tuple(gw.shape) == (n_pad, k_pad)):
                 return gw, gb, True
             return (torch.zeros((n_pad, k_pad), device=dev, dtype=torch.float32),
                     torch.zeros((n_pad,), device=dev, dtype=torch.float32), False)
@@ -144,12 +156,36 @@ class _MLPFunction(torch.autograd.Function):
         targets = [grad_targets(mlp.trunk[l][0], layers[l][0].shape[0], layers[l][0].shape[1]) for l in range(L)]
         dWh = torch.zeros((64, Wh.shape[1]), device=dev, dtype=torch.float32)
         dbh = torch.zeros((64,), device=dev, dtype=torch.float32)
-        if _lib.PROFILE is not None:
+
+        def finish_layer(l):
+            """direct mode: fold padded scratch into .grad, then tell the trainer the bucket is complete."""
+            if not direct:
+                return
+            dW, db, in_place = targets[l]
+            lin = mlp.trunk[l][0]
+            if not in_place:
+                lin.weight.grad.add_(dW[: lin.out_features, : lin.in_features])
+                lin.bias.grad.add_(db[: lin.out_features])
+            if l == L - 1:
+                r = 0
+                for h in mlp.heads:
+                    n = h.out_features
+                    h.weight.grad.add_(dWh[r:r + n, : h.in_features])
+                    h.bias.grad.add_(dbh[r:r + n])
+                    r += n
+            if mlp.grad_hook is not None:
+                mlp.grad_hook(l)
+
+        per_layer = _lib.PROFILE is not None or (direct and mlp.grad_hook is not None)
+        if per_layer:
+            # one C call per GEMM: instrumented runs (bench.py's per-kernel table) and the data-parallel trainer,
+            # which starts the all-reduce of a layer's gradients as soon as its wgrad has been enqueued
             dzh = ops.head_grad_pack(g_out, out if mlp.head_act == ACT_SIGMOID else None, mlp.head_act)
             ops.linear_wgrad(dzh, saved[L], dW=dWh, db=dbh)
             dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
-            for l in range(L, 0, -1):  # trunk layer l maps saved[l-1] -> saved[l]
+            for l in range(L, 0, -1):  # trunk layer l-1 maps saved[l-1] -> saved[l]
                 ops.linear_wgrad(dz, saved[l - 1], dW=targets[l - 1][0], db=targets[l - 1][1])
+                finish_layer(l - 1)
                 if l > 1:
                     dz = ops.linear_dgrad(dz, layers[l - 1][1], saved[l - 1], acts[l - 2])
         else:
@@ -165,22 +201,29 @@ class _MLPFunction(torch.autograd.Function):
             _lib.call("mip360_mlp_bwd", g.data_ptr(), out.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
                       ctypes.byref(head), mlp.n_valid, act_ptrs, dW_ptrs, db_ptrs, dzh.data_ptr(), dz0.data_ptr(),
                       dz1.data_ptr())
+            for l in range(L - 1, -1, -1):
+                finish_layer(l)
+        if direct:  # everything has been added to .grad; autograd has nothing left to accumulate
+            return (None, None, None) + (None,) * (2 * L + 2 * len(mlp.heads))
         grads_trunk = []
-        for (dW, db, direct), (lin, _) in zip(targets, mlp.trunk):
-            # direct: already accumulated into .grad; returning None tells autograd there is nothing left to add
-            grads_trunk += [None, None] if direct else [dW[: lin.out_features, : lin.in_features], db[: lin.out_features]]
+        for (dW, db, _), (lin, _) in zip(targets, mlp.trunk):
+            grads_trunk += [dW[: lin.out_features, : lin.in_features], db[: lin.out_features]]
         grads_head = []
         r = 0
         for h in mlp.heads:
             n = h.out_features
             grads_head += [dWh[r:r + n, : h.in_features], dbh[r:r + n]]
             r += n
-        return (None, None, *grads_trunk, *grads_head)
+        return (None, None, None, *grads_trunk, *grads_head)
 
 
 def mlp_apply(mlp: PackedMLP, x):
-    """Run the packed MLP on bf16 rows x [M,64]; differentiable w.r.t. the fp32 master parameters."""
-    return _MLPFunction.apply(x, mlp, *mlp.params())
+    """Run the packed MLP on bf16 rows x [M,64]; differentiable w.r.t. the fp32 master parameters.
+    Under torch.no_grad() (render_image, eval, the detached forwards of train.py:55,68-70) only two ping-pong
+    activation buffers are allocated and nothing is saved."""
+    params = mlp.params()
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _MLPFunction.apply(x, mlp, need_grad, *params)
 
 
 def pack_prop(model_seq):

@@ -18,11 +18,6 @@ from mipnerf360_b200.intern.encoding import PositionalEncoding, ViewdirectionEnc
 from mipnerf360_b200.intern.ray import namedtuple_map
 
 
-# With torch.distributed initialised, all-reduce the batch-coupled contraction norm so that a ray-sharded
-# forward equals the unsharded one.  Rendering shards set this to False (independent chunks).
-SYNC_BATCH_STATS = True
-
-
 def _kaiming_init(model):
     """model.py:8-12."""
     for module in model.modules():
@@ -30,20 +25,23 @@ def _kaiming_init(model):
             nn.init.kaiming_uniform_(module.weight)
 
 
-def _encode(rays, t_vals, viewdirs_encoding, contract_mode):
+def _encode(rays, t_vals, viewdirs_encoding, contract_mode, batch_group=None):
     """cast -> Gaussian -> contract -> IPE ++ view-direction encoding, straight to bf16 MLP rows
-    (model.py:82-88 / 169-176 without materialising means, covs or the [B,N,58] fp32 tensor)."""
+    (model.py:82-88 / 169-176 without materialising means, covs or the [B,N,58] fp32 tensor).
+
+    batch_group: None (default) = this call is the whole batch, like the reference.  A torch.distributed process
+    group = the call is one ray shard of a data-parallel batch: the reference's batch-global contraction norm
+    (App. A1) is summed over the group so that the sharded forward equals the unsharded one.  Only
+    train.Trainer sets it; model(rays) / render_image never issue a collective."""
     vd = viewdirs_encoding(rays.viewdirs)
     if vd.shape[-1] != 16:
         raise ValueError("the fused encoder packs 16 view-direction features (viewdir_min_deg=0, viewdir_max_deg=4)")
     norm_sq = None
-    if contract_mode == ops.CONTRACT_REFERENCE and SYNC_BATCH_STATS and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size() > 1:
-        # ray-sharded run: the reference's contraction norm is over the WHOLE batch (App. A1), i.e. all ranks
+    if contract_mode == ops.CONTRACT_REFERENCE and batch_group is not None:
         t = ops.f32c(t_vals)
         B, N = t.shape[0], t.shape[1] - 1
         norm_sq = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, ops.f32c(rays.directions), B, N)
-        dist.all_reduce(norm_sq, op=dist.ReduceOp.SUM)
+        dist.all_reduce(norm_sq, op=dist.ReduceOp.SUM, group=batch_group)
     return ops.cast_ipe(t_vals, rays.origins, rays.directions, rays.radii, vd, contract_mode=contract_mode,
                         norm_sq=norm_sq, want_x=True)["x"]
 
@@ -60,6 +58,7 @@ class prop_net(nn.Module):
         self.viewdir_max_deg = viewdir_max_deg
         self.device = device
         self.contract_mode = ops.CONTRACT_REFERENCE
+        self.batch_group = None  # see _encode; set by train.Trainer for ray-sharded training only
 
         self.positional_encoding = PositionalEncoding()
         self.viewdirs_encoding = ViewdirectionEncoding(self.viewdir_min_deg, self.viewdir_max_deg)
@@ -85,7 +84,7 @@ class prop_net(nn.Module):
         """model.py:80-94 -> (t_vals [B,N+1], weights [B,N])."""
         B = rays.origins.shape[0]
         t_vals = ops.level0_t_vals(rays.near, rays.far, self.num_samples, self.randomized)
-        x = _encode(rays, t_vals, self.viewdirs_encoding, self.contract_mode)
+        x = _encode(rays, t_vals, self.viewdirs_encoding, self.contract_mode, self.batch_group)
         raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 1] logits
         weights = ops.density_to_weight(t_vals, raw.view(B, self.num_samples), rays.directions, raw_logits=True,
                                         density_bias=self.density_bias)
@@ -108,6 +107,7 @@ class nerf_net(nn.Module):
         self.viewdir_max_deg = viewdir_max_deg
         self.device = device
         self.contract_mode = ops.CONTRACT_REFERENCE
+        self.batch_group = None  # see _encode
 
         self.positional_encoding = PositionalEncoding()
         self.viewdirs_encoding = ViewdirectionEncoding(self.viewdir_min_deg, self.viewdir_max_deg)
@@ -131,7 +131,7 @@ class nerf_net(nn.Module):
         B = rays.origins.shape[0]
         new_t = ops.resample(t_vals, coarse_weights, self.randomized, self.resample_padding)
         N = new_t.shape[1] - 1
-        x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode)
+        x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode, self.batch_group)
         raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 4] = (density head, colour head), post-sigmoid
         comp_rgb, distance, acc, weights = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions,
                                                                self.density_bias, self.rgb_padding, self.white_bkgd)

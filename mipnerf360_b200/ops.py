@@ -225,6 +225,7 @@ class _Composite(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd):
+        ctx.set_materialize_grads(False)  # unused outputs (distance, acc in training) arrive as None, not zeros
         B, N = t_vals.shape[0], t_vals.shape[1] - 1
         comp, dist, acc = _empty((B, 3), t_vals), _empty((B,), t_vals), _empty((B,), t_vals)
         w = _empty((B, N), t_vals)
@@ -232,7 +233,6 @@ class _Composite(torch.autograd.Function):
              density_bias, rgb_padding, int(white_bkgd), ptr(comp), ptr(dist), ptr(acc), ptr(w))
         ctx.save_for_backward(rgb_or_raw, density, t_vals, dirs)
         ctx.cfg = (head_mode, density_bias, rgb_padding, int(white_bkgd))
-        ctx.mark_non_differentiable(dist)
         return comp, dist, acc, w
 
     @staticmethod
@@ -242,6 +242,7 @@ class _Composite(torch.autograd.Function):
         B, N = t_vals.shape[0], t_vals.shape[1] - 1
         g_comp = f32c(g_comp) if g_comp is not None else None
         g_acc = f32c(g_acc) if g_acc is not None else None
+        g_dist = f32c(g_dist) if g_dist is not None else None
         g_w = f32c(g_w) if g_w is not None else None
         if head_mode == 1:
             g_raw = torch.empty_like(rgb_or_raw)
@@ -250,15 +251,24 @@ class _Composite(torch.autograd.Function):
             g_raw = None
             g_rgb_in, g_density = torch.empty_like(rgb_or_raw), torch.empty_like(density)
         call("mip360_composite_bwd", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
-             density_bias, rgb_padding, white, ptr(g_comp), ptr(g_acc), ptr(g_w), ptr(g_rgb_in), ptr(g_density),
-             ptr(g_raw))
+             density_bias, rgb_padding, white, ptr(g_comp), ptr(g_acc), ptr(g_dist), ptr(g_w), ptr(g_rgb_in),
+             ptr(g_density), ptr(g_raw))
         if head_mode == 1:
             return g_raw, None, None, None, None, None, None, None
         return g_rgb_in, g_density, None, None, None, None, None, None
 
 
+def _no_grad_inputs(who, **tensors):
+    for name, t in tensors.items():
+        if t.requires_grad:
+            raise _lib.Mip360Error(f"{who}: {name} must not require grad (rays and sample positions carry no gradient "
+                                   "in the reference: resampling runs under no_grad, ray.py:136)")
+
+
 def composite(rgb, density, t_vals, dirs, white_bkgd):
-    """volumetric_rendering(rgb [B,N,3], density [B,N,1] or [B,N], t_vals, dirs, white_bkgd)."""
+    """volumetric_rendering(rgb [B,N,3], density [B,N,1] or [B,N], t_vals, dirs, white_bkgd).  comp_rgb, distance,
+    acc and weights are differentiable w.r.t. rgb and density."""
+    _no_grad_inputs("composite", t_vals=t_vals, dirs=dirs)
     rgb, t_vals, dirs = f32c(rgb), f32c(t_vals), f32c(dirs)
     density = f32c(density.reshape(density.shape[0], density.shape[1]))
     check_cuda(rgb, density, t_vals, dirs)
@@ -352,6 +362,10 @@ class _Distortion(torch.autograd.Function):
 
 
 def distortion_loss(s_vals, weights):
+    if s_vals.requires_grad:
+        # the reference's s_vals never carries a gradient (resampling runs under no_grad, ray.py:136); refuse
+        # instead of silently returning a zero gradient for it
+        raise _lib.Mip360Error("distortion_loss: s_vals must not require grad (only the weights are differentiated)")
     s_vals, weights = f32c(s_vals), f32c(weights)
     check_cuda(s_vals, weights)
     return _Distortion.apply(s_vals.detach(), weights)
@@ -484,19 +498,21 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
 # ------------------------------------------------------------------------------------------------
 # ray generation
 # ------------------------------------------------------------------------------------------------
-def generate_rays(cam_to_world, h, w, focal, near, far, ndc=False, ndc_near=1.0):
+def generate_rays(cam_to_world, h, w, focal, near, far, ndc=False, ndc_near=1.0, ray_begin=0, ray_count=None):
     """dataset.py:109-145 (pinhole) / dataset.py:364-387 (LLFF NDC), flattened as dataset.py:147-152.
-    cam_to_world [n, >=3, 4] device tensor -> Rays of [n*h*w, c] device tensors; nothing is built on the host."""
+    cam_to_world [n, >=3, 4] device tensor -> Rays of [n*h*w, c] device tensors; nothing is built on the host.
+    ray_begin / ray_count select a slab of the flattened ray index (a render chunk, a rank's partition)."""
     from mipnerf360_b200.intern.ray import Rays
     c2w = f32c(cam_to_world)
     check_cuda(c2w)
     if c2w.dim() == 2:
         c2w = c2w[None]
-    n = c2w.shape[0] * h * w
+    total = c2w.shape[0] * h * w
+    n = total - ray_begin if ray_count is None else int(ray_count)
     o, d, v = _empty((n, 3), c2w), _empty((n, 3), c2w), _empty((n, 3), c2w)
     r, nr, fr = _empty((n, 1), c2w), _empty((n, 1), c2w), _empty((n, 1), c2w)
-    call("mip360_generate_rays", ptr(c2w), c2w.shape[1], c2w.shape[0], int(h), int(w), float(focal), float(near),
-         float(far), int(bool(ndc)), float(ndc_near), ptr(o), ptr(d), ptr(v), ptr(r), ptr(nr), ptr(fr))
+    call("mip360_generate_rays_range", ptr(c2w), c2w.shape[1], c2w.shape[0], int(h), int(w), float(focal), float(near),
+         float(far), int(bool(ndc)), float(ndc_near), int(ray_begin), n, ptr(o), ptr(d), ptr(v), ptr(r), ptr(nr), ptr(fr))
     return Rays(o, d, v, r, nr, fr)
 
 

@@ -8,10 +8,13 @@ hot path is its call pattern, reproduced by `Trainer.step`:
           AdamW step, scheduler step ]
 
 Parameters of each net live in one flat fp32 buffer (the nn.Parameters are views), gradients in another:
-AdamW is one fused kernel launch per net and the data-parallel gradient exchange is one
-NCCL all-reduce per net over NVLink.  With world_size > 1 the reference's batch-coupled scalars (global
-contraction norm, App. A1; batch-total proposal bounds, App. A6) are all-reduced too, so a sharded step
-computes what the unsharded reference step computes on the concatenated batch.
+AdamW and the bf16 re-cast of the GEMM operands are ONE fused kernel launch per net.
+
+Data parallel: one process per GPU, the ray batch is sharded, weights are replicated.  Gradients are
+all-reduced over NCCL per layer bucket, last layer first, on a side stream, while the remaining dgrad / wgrad
+GEMMs of the backward pass run.  The reference's batch-coupled scalars (global contraction norm, App. A1;
+batch-total proposal bounds, App. A6; the squared error inside Loss_nerf's log) are all-reduced too, so a sharded
+step computes what the unsharded reference step computes on the concatenated batch.
 """
 from __future__ import annotations
 
@@ -48,31 +51,46 @@ def sharded_loss_nerf(rgb, pixels, world, group=None):
 
 class FlatAdamW:
     """torch.optim.AdamW semantics (train.py:38) over per-net flat buffers.  Like torch >= 2.0, parameters
-    without a gradient are skipped: `step(names)` updates only the nets that were just back-propagated."""
+    without a gradient are skipped: `step(names)` updates only the nets that were just back-propagated.
+
+    groups: {name: nn.Module}.  The parameters of each module are re-pointed at views of one flat fp32 buffer
+    (values preserved) and receive preallocated .grad views of a second one.  Every `mlp.PackedMLP` found on the
+    modules (attribute `_packed`) is switched to direct gradient accumulation and is refreshed by `step` — the
+    update kernel writes through raw pointers, which autograd's version counters do not see."""
 
     def __init__(self, groups, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.groups = {}
-        self.on_step = {}
         for name, module in groups.items():
             params = list(module.parameters())
             n = sum(p.numel() for p in params)
             dev = params[0].device
             flat = torch.empty(n, device=dev, dtype=torch.float32)
             grad = torch.zeros(n, device=dev, dtype=torch.float32)
-            off = 0
+            off, offsets = 0, {}
             for p in params:
                 k = p.numel()
                 flat[off:off + k].copy_(p.data.reshape(-1))
                 p.data = flat[off:off + k].view_as(p)
                 p.grad = grad[off:off + k].view_as(p)
+                offsets[id(p)] = (off, k)
                 off += k
+            packed = [m._packed for m in module.modules() if hasattr(m, "_packed")]
+            for pk in packed:
+                pk.direct_grad = True
             self.groups[name] = dict(params=params, flat=flat, grad=grad, m=torch.zeros_like(flat),
-                                     v=torch.zeros_like(flat), step=0)
+                                     v=torch.zeros_like(flat), step=0, offsets=offsets, packed=packed)
 
-    def zero_grad(self):
-        for g in self.groups.values():
-            g["grad"].zero_()
+    def span(self, name, params):
+        """[lo, hi) of the flat buffer covered by `params` (which must be adjacent in it)."""
+        offs = sorted(self.groups[name]["offsets"][id(p)] for p in params)
+        for (a, n), (b, _) in zip(offs, offs[1:]):
+            assert a + n == b, "parameters of one bucket must be contiguous in the flat buffer"
+        return offs[0][0], offs[-1][0] + offs[-1][1]
+
+    def zero_grad(self, names=None):
+        for name in (names or self.groups):
+            self.groups[name]["grad"].zero_()
 
     def step(self, names, lr=None):
         for name in names:
@@ -80,32 +98,119 @@ class FlatAdamW:
             g["step"] += 1
             ops.adamw_step(g["flat"], g["grad"], g["m"], g["v"], self.lr if lr is None else lr, self.betas[0],
                            self.betas[1], self.eps, self.wd, g["step"])
-            for cb in self.on_step.get(name, ()):
-                cb()  # e.g. PackedMLP.invalidate: the kernel wrote through the flat buffer, not through autograd
+            for pk in g["packed"]:
+                pk.invalidate()
+
+    # -- checkpoint round trip (train.py:39-41,98-103: optimizer.state_dict() <-> optim.pt) ----------------------
+    def state_dict(self):
+        """The layout torch.optim.AdamW(model.parameters()) produces for the same parameters in the same order, so
+        optim_{step}.pt files are interchangeable with the reference's."""
+        state, idx = {}, 0
+        for g in self.groups.values():
+            for p in g["params"]:
+                off, k = g["offsets"][id(p)]
+                if g["step"] > 0:
+                    state[idx] = dict(step=torch.tensor(float(g["step"])),
+                                      exp_avg=g["m"][off:off + k].view_as(p).clone(),
+                                      exp_avg_sq=g["v"][off:off + k].view_as(p).clone())
+                idx += 1
+        group = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, amsgrad=False, maximize=False,
+                     foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True,
+                     params=list(range(idx)))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        pg = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.wd = pg["lr"], tuple(pg["betas"]), pg["eps"], pg["weight_decay"]
+        idx = 0
+        for g in self.groups.values():
+            steps = set()
+            for p in g["params"]:
+                off, k = g["offsets"][id(p)]
+                st = sd["state"].get(idx)
+                if st is None:
+                    g["m"][off:off + k].zero_()
+                    g["v"][off:off + k].zero_()
+                    steps.add(0)
+                else:
+                    g["m"][off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    g["v"][off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(st["step"]))
+                idx += 1
+            if len(steps) != 1:
+                raise ValueError("FlatAdamW keeps one step count per net; the checkpoint has mixed counts " + str(steps))
+            g["step"] = steps.pop()
 
 
 class Trainer:
+    """One reference training iteration per `step` (train.py:52-82), single GPU or data parallel.
+
+    group: torch.distributed process group of the data-parallel ranks (default: the world when initialised).
+    data_parallel=False: ignore torch.distributed (every rank trains on its own, whole, batch).
+    overlap: bucket the gradient all-reduce per layer and overlap it with the rest of the backward pass."""
+
     def __init__(self, model, lr_init=2e-3, lr_final=2e-5, max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.1,
-                 weight_decay=1e-5, dist_weight_decay=0.01):
+                 weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=True):
         self.model = model
         self.sched = dict(lr_init=lr_init, lr_final=lr_final, max_steps=max_steps, lr_delay_steps=lr_delay_steps,
                           lr_delay_mult=lr_delay_mult)
         self.opt = FlatAdamW({"prop": model.prop_net, "nerf": model.nerf_net}, lr_init, weight_decay)
-        self.opt.on_step = {"prop": [model.prop_net._packed.invalidate], "nerf": [model.nerf_net._packed.invalidate]}
         self.dist_weight_decay = dist_weight_decay
         self.sched_step = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.group = group
+        self.world = dist.get_world_size(group) if data_parallel and dist.is_available() and dist.is_initialized() else 1
+        self.overlap = bool(overlap) and self.world > 1
+        self._pending = []
+        if self.world > 1:
+            if group is None:
+                self.group = dist.group.WORLD
+            # ray-sharded batch: the nets sum the batch-global contraction norm over the group (model._encode)
+            model.prop_net.batch_group = self.group
+            model.nerf_net.batch_group = self.group
+            if self.overlap:
+                self.comm_stream = torch.cuda.Stream()
+                for name, net in (("prop", model.prop_net), ("nerf", model.nerf_net)):
+                    net._packed.grad_hook = self._make_hook(name, net._packed)
+
+    # -- gradient exchange ---------------------------------------------------------------------------------------
+    def _make_hook(self, name, pk):
+        """Bucket = the gradients completed by one wgrad: trunk layer l (plus the heads for the last trunk layer,
+        whose wgrad runs first).  Issued from the backward pass right after that wgrad was enqueued."""
+        L = len(pk.trunk)
+        spans = []
+        for l in range(L):
+            ps = [pk.trunk[l][0].weight, pk.trunk[l][0].bias]
+            if l == L - 1:
+                for h in pk.heads:
+                    ps += [h.weight, h.bias]
+            spans.append(self.opt.span(name, ps))
+        grad = self.opt.groups[name]["grad"]
+
+        def hook(l):
+            lo, hi = spans[l]
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            self._pending.append(name)
+        return hook
+
+    def _finish_grads(self, name):
+        if self.world == 1:
+            return
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._pending.clear()
+        else:
+            dist.all_reduce(self.opt.groups[name]["grad"], op=dist.ReduceOp.SUM, group=self.group)
 
     # -- pieces ------------------------------------------------------------------------------------
     def _lr(self):
         return lr_at(self.sched_step, **self.sched)
 
-    def _allreduce_grads(self, name):
-        if self.world > 1:
-            dist.all_reduce(self.opt.groups[name]["grad"], op=dist.ReduceOp.SUM)
-
     def _optim(self, name):
-        self._allreduce_grads(name)
+        self._finish_grads(name)
         self.opt.step([name], lr=self._lr())
         self.sched_step += 1  # scheduler.step() after every optimizer.step() (train.py:64,82; App. A11)
 
@@ -115,38 +220,50 @@ class Trainer:
         total = ops.bounds_total(b)
         batch = float(w_hat.shape[0])
         if self.world > 1:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
             batch *= self.world
         return ops.interlevel_loss(w_hat, bound_total=total, batch_div=batch)
 
     def _loss_nerf(self, rgb, pixels):
         if self.world == 1:
             return Loss_nerf(rgb, pixels)
-        return sharded_loss_nerf(rgb, pixels, self.world)
+        return sharded_loss_nerf(rgb, pixels, self.world, self.group)
 
     # -- one reference iteration -------------------------------------------------------------------
-    def step(self, rays, pixels):
-        """train.py:52-82 on device-resident rays/pixels.  Returns (loss_prop, loss_all, psnr) as device scalars."""
+    def prop_substep(self, rays):
+        """train.py:54-64: one proposal update.  Returns the loss (device scalar)."""
         m = self.model
-        loss_prop = None
-        for _ in range(2):
-            t_hat, w_hat = m.prop_net.forward(rays)
-            with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
-                _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
-            loss_prop = self._loss_prop(t, w, t_hat, w_hat)
-            self.opt.zero_grad()
-            loss_prop.backward()
-            self._optim("prop")
+        t_hat, w_hat = m.prop_net.forward(rays)
+        with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
+            _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
+        loss_prop = self._loss_prop(t, w, t_hat, w_hat)
+        self.opt.zero_grad(["prop"])
+        loss_prop.backward()
+        self._optim("prop")
+        return loss_prop.detach()
+
+    def nerf_substep(self, rays, pixels):
+        """train.py:68-82: the NeRF update.  Returns (loss_all, psnr) (device scalars).  Data parallel: psnr and the
+        photometric part of loss_all are those of the whole batch, the distortion part is the local shard's sum."""
+        m = self.model
         with torch.no_grad():
             t_hat, w_hat = m.prop_net.forward(rays)
         rgb, _, _, t, w, s = m.nerf_net.forward(rays, t_hat, w_hat)
         loss_nerf, psnr = self._loss_nerf(rgb, pixels)
         loss_dist = Loss_dist(s, w)
         loss_all = loss_nerf + self.dist_weight_decay * loss_dist
-        self.opt.zero_grad()
+        self.opt.zero_grad(["nerf"])
         loss_all.backward()
         self._optim("nerf")
-        return loss_prop.detach(), loss_all.detach(), psnr.detach()
+        return loss_all.detach(), psnr.detach()
+
+    def step(self, rays, pixels):
+        """train.py:52-82 on device-resident rays/pixels.  Returns (loss_prop, loss_all, psnr) as device scalars."""
+        loss_prop = None
+        for _ in range(2):
+            loss_prop = self.prop_substep(rays)
+        loss_all, psnr = self.nerf_substep(rays, pixels)
+        return loss_prop, loss_all, psnr
 
     def step_host(self, rays_host, pixels_host):
         """Same, from pinned host buffers: H2D copy of the batch, the iteration, D2H read of the losses."""
@@ -155,3 +272,45 @@ class Trainer:
         pixels = pixels_host.to(dev, non_blocking=True)
         lp, la, psnr = self.step(rays, pixels)
         return torch.stack([lp, la, psnr]).cpu()
+
+
+def check_sharded_equals_unsharded(device, rays_per_rank=512, num_samples=64, hidden_proposal=256, hidden_nerf=1024,
+                                   overlap=True, seed=0):
+    """Run under torch.distributed (NCCL, one rank per GPU).  One training iteration on a ray-sharded batch (data
+    parallel: sharded rays, all-reduced gradients and batch-coupled scalars) against the same iteration on the
+    whole batch computed by this rank alone, same initial weights.  Deterministic sampling, so that shards and
+    whole batch take the same samples, and a vanishing learning rate, so that the three sub-steps of both runs see
+    the same weights.  Returns a dict of relative errors (losses; per-net gradient, Frobenius)."""
+    from mipnerf360_b200.model import mipNeRF360
+    from mipnerf360_b200.synthetic import generic_rays
+    world, rank = dist.get_world_size(), dist.get_rank()
+    B = rays_per_rank * world
+    rays, pixels = generic_rays(B, 4242 + seed, device=device)  # the same global batch on every rank
+    sl = slice(rank * rays_per_rank, (rank + 1) * rays_per_rank)
+    models = []
+    for _ in range(2):
+        torch.manual_seed(seed)
+        models.append(mipNeRF360(randomized=False, num_samples=num_samples, hidden_proposal=hidden_proposal,
+                                 hidden_nerf=hidden_nerf, device=device))
+    kw = dict(lr_init=1e-12, lr_final=1e-12)
+    dp = Trainer(models[0], overlap=overlap, **kw)
+    solo = Trainer(models[1], data_parallel=False, **kw)
+    out = {}
+    lp_a = dp.prop_substep(Rays(*[r[sl] for r in rays]))
+    lp_b = solo.prop_substep(rays)
+    la_a, ps_a = dp.nerf_substep(Rays(*[r[sl] for r in rays]), pixels[sl])
+    la_b, ps_b = solo.nerf_substep(rays, pixels)
+    torch.cuda.synchronize()
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    out["loss_prop"] = rel(lp_a, lp_b)
+    # loss_all = Loss_nerf (global, through the all-reduced squared error) + 0.01 * Loss_dist of the LOCAL shard:
+    # the distortion term is a plain sum over rays (App. A9), so the global value is the sum of the shards' terms
+    ln_a = 30 - ps_a
+    dist_part = (la_a - ln_a).clone()
+    dist.all_reduce(dist_part)
+    out["loss_all"] = rel(ln_a + dist_part, la_b)
+    out["psnr"] = rel(ps_a, ps_b)
+    for name in ("prop", "nerf"):
+        out["grad_" + name] = rel(dp.opt.groups[name]["grad"], solo.opt.groups[name]["grad"])
+    out["world"] = world
+    return out

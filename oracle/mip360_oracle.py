@@ -89,10 +89,15 @@ def contract_jacobian(x):
     return torch.where(m <= 1, eye, jac)
 
 
-def gaussian_to_xyz(d, t_mean, t_var, r_var):
-    """intern/parameterization.py:31-62, full-covariance branch (diag=False is the only one used)."""
+def gaussian_to_xyz(d, t_mean, t_var, r_var, diag=False):
+    """intern/parameterization.py:31-62: full covariance [B,N,3,3] (the branch the model uses) or, with diag=True,
+    its diagonal [B,N,3] (:49-53)."""
     mean = d[..., None, :] * t_mean[..., None]
     d_mag_sq = torch.clamp(torch.sum(d**2, dim=-1, keepdim=True), min=1e-10)
+    if diag:
+        d_outer_diag = d**2
+        null_outer_diag = 1 - d_outer_diag / d_mag_sq
+        return mean, t_var[..., None] * d_outer_diag[..., None, :] + r_var[..., None] * null_outer_diag[..., None, :]
     d_outer = d[..., :, None] * d[..., None, :]
     eye = torch.eye(3, dtype=d.dtype, device=d.device)
     null_outer = eye - d[..., :, None] * (d / d_mag_sq)[..., None, :]
@@ -114,8 +119,13 @@ def gaussian_contract(mean, cov, norm_sq=None):
     return mean_c, cov_c
 
 
-def frustum_moments(t0, t1, radii):
-    """intern/parameterization.py:101-107 (stable branch)."""
+def frustum_moments(t0, t1, radii, stable=True):
+    """intern/parameterization.py:100-113: the stable formula of the mip-NeRF paper, or the original one."""
+    if not stable:
+        t_mean = (3 * (t1**4 - t0**4)) / (4 * (t1**3 - t0**3))
+        r_var = radii**2 * (3 / 20 * (t1**5 - t0**5) / (t1**3 - t0**3))
+        t_mosq = 3 / 5 * (t1**5 - t0**5) / (t1**3 - t0**3)
+        return t_mean, t_mosq - t_mean**2, r_var
     mu = (t0 + t1) / 2
     hw = (t1 - t0) / 2
     t_mean = mu + (2 * mu * hw**2) / (3 * mu**2 + hw**2)
@@ -124,9 +134,10 @@ def frustum_moments(t0, t1, radii):
     return t_mean, t_var, r_var
 
 
-def conical_frustum_to_gaussian(d, t0, t1, radii, norm_sq=None):
-    """intern/parameterization.py:85-117."""
-    t_mean, t_var, r_var = frustum_moments(t0, t1, radii)
+def conical_frustum_to_gaussian(d, t0, t1, radii, norm_sq=None, stable=True):
+    """intern/parameterization.py:85-117 (diag=False; with diag=True the reference itself fails inside
+    gaussian_contract: a [B,N,3] diagonal cannot be multiplied by the [B,N,3,3] Jacobians)."""
+    t_mean, t_var, r_var = frustum_moments(t0, t1, radii, stable)
     mean, cov = gaussian_to_xyz(d, t_mean, t_var, r_var)
     return gaussian_contract(mean, cov, norm_sq)
 
@@ -276,6 +287,12 @@ def integrated_pos_enc(mean, cov):
     return torch.cat((damp * torch.sin(gamma), damp * torch.cos(gamma)), -1)
 
 
+def pos_enc(mean):
+    """intern/encoding.py:57-60 — the branch without a covariance: plain sin / cos of the 21 projections."""
+    gamma = torch.matmul(mean, basis(mean.dtype, mean.device).T)
+    return torch.cat((torch.sin(gamma), torch.cos(gamma)), -1)
+
+
 def viewdir_enc(viewdirs, min_deg=0, max_deg=4):
     """intern/encoding.py:69-90 — arccos(z), arctan(y/(x+1e-6)) (App. A10)."""
     scales = torch.tensor([2.0**i for i in range(min_deg, max_deg)], dtype=viewdirs.dtype, device=viewdirs.device)
@@ -285,10 +302,10 @@ def viewdir_enc(viewdirs, min_deg=0, max_deg=4):
     return torch.cat((torch.sin(theta), torch.cos(theta), torch.sin(phi), torch.cos(phi)), -1)
 
 
-def mlp_input(mean, cov, viewdirs):
-    """model.py:85-88 / 173-176: [B,N,42] IPE ++ [B,16] view-dir encoding repeated along N (App. A12)."""
+def mlp_input(mean, cov, viewdirs, min_deg=0, max_deg=4):
+    """model.py:85-88 / 173-176: [B,N,42] IPE ++ [B,4*(max-min)] view-dir encoding repeated along N (App. A12)."""
     enc = integrated_pos_enc(mean, cov)
-    vd = viewdir_enc(viewdirs)[:, None, :].expand(-1, enc.shape[1], -1)
+    vd = viewdir_enc(viewdirs, min_deg, max_deg)[:, None, :].expand(-1, enc.shape[1], -1)
     return torch.cat((enc, vd), -1)
 
 
@@ -401,21 +418,21 @@ def nerf_mlp(sd, x):
     return raw_density, raw_rgb
 
 
-def prop_forward(sd, rays, num_samples, randomized, density_bias=-1.0, t_rand=None):
+def prop_forward(sd, rays, num_samples, randomized, density_bias=-1.0, t_rand=None, viewdir_deg=(0, 4)):
     """model.py:80-94."""
     t, (mean, cov) = sample_along_rays(rays.origins, rays.directions, rays.radii, num_samples,
                                        rays.near, rays.far, randomized, t_rand)
-    raw = prop_mlp(sd, mlp_input(mean, cov, rays.viewdirs))
+    raw = prop_mlp(sd, mlp_input(mean, cov, rays.viewdirs, *viewdir_deg))
     density = F.softplus(raw + density_bias)
     return t, density_to_weight(t, density[..., 0], rays.directions)
 
 
 def nerf_forward(sd, rays, t_vals, coarse_weights, randomized, density_bias=-1.0, rgb_padding=0.001,
-                 resample_padding=0.01, white_bkgd=False, jitter=None):
+                 resample_padding=0.01, white_bkgd=False, jitter=None, viewdir_deg=(0, 4)):
     """model.py:163-200.  Returns (rgb, dist, acc, t_vals(+1e-6 as the reference returns it), weights, s_vals)."""
     t, (mean, cov) = resample_along_rays(rays.origins, rays.directions, rays.radii, t_vals, coarse_weights,
                                          randomized, resample_padding, jitter)
-    raw_density, raw_rgb = nerf_mlp(sd, mlp_input(mean, cov, rays.viewdirs))
+    raw_density, raw_rgb = nerf_mlp(sd, mlp_input(mean, cov, rays.viewdirs, *viewdir_deg))
     rgb = raw_rgb * (1 + 2 * rgb_padding) - rgb_padding
     density = F.softplus(raw_density + density_bias)
     comp_rgb, distance, acc, weights = volumetric_rendering(rgb, density, t, rays.directions, white_bkgd)
@@ -425,8 +442,80 @@ def nerf_forward(sd, rays, t_vals, coarse_weights, randomized, density_bias=-1.0
 
 def model_forward(sd, rays, num_samples, randomized, t_rand=None, jitter=None, **kw):
     """model.py:247-252."""
-    t_hat, w_hat = prop_forward(sd, rays, num_samples, randomized, kw.get("density_bias", -1.0), t_rand)
+    t_hat, w_hat = prop_forward(sd, rays, num_samples, randomized, kw.get("density_bias", -1.0), t_rand,
+                                viewdir_deg=kw.get("viewdir_deg", (0, 4)))
     return nerf_forward(sd, rays, t_hat, w_hat, randomized, jitter=jitter, **kw)[:3]
+
+
+def to8b(img):
+    """intern/utils.py:17-21 (NumPy): (255 * clip(nan_to_num(x), 0, 1)).astype(uint8), any rank."""
+    import numpy as np
+    return (255 * np.clip(np.nan_to_num(np.asarray(img)), 0, 1)).astype(np.uint8)
+
+
+def render_image(sd, rays, height, width, num_samples, chunks=4096, randomized=False, **kw):
+    """model.py:254-274: the chunk loop (each chunk is its own batch for the batch-global contraction norm,
+    App. A1), to8b on the colours.  Returns (uint8 [h,w,3], float rgb [h,w,3], dist [h,w], acc [h,w])."""
+    n = rays[0].shape[0]
+    outs = []
+    with torch.no_grad():
+        for i in range(0, n, chunks):
+            outs.append(model_forward(sd, Rays(*[r[i:i + chunks] for r in rays]), num_samples, randomized, **kw))
+    rgb = torch.cat([o[0] for o in outs]).reshape(height, width, 3)
+    dist = torch.cat([o[1] for o in outs]).reshape(height, width)
+    acc = torch.cat([o[2] for o in outs]).reshape(height, width)
+    return to8b(rgb.numpy()), rgb, dist, acc
+
+
+def lr_at(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
+    """intern/scheduler.py:13-23 at scheduler step `step`."""
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    else:
+        delay = 1.0
+    t = min(max(step / max_steps, 0), 1)
+    return delay * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
+def train_loop(sd, rays, pixels, num_samples, iterations, randomized=False, dist_weight=0.01, weight_decay=1e-5,
+               lr_init=2e-3, lr_final=2e-5, max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.1):
+    """train.py:38-82: AdamW over ALL parameters (those without a gradient are skipped), lr_decay stepped after every
+    optimiser step, 2 proposal sub-steps + 1 NeRF sub-step per iteration.  Returns (final params, log rows
+    [loss_prop, loss_nerf, loss_dist, loss_all, psnr, lr])."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=lr_init, weight_decay=weight_decay)
+    cfg = dict(lr_init=lr_init, lr_final=lr_final, max_steps=max_steps, lr_delay_steps=lr_delay_steps,
+               lr_delay_mult=lr_delay_mult)
+    sched_step = 0
+
+    def set_lr():
+        for gch in opt.param_groups:
+            gch["lr"] = lr_at(sched_step, **cfg)
+
+    set_lr()  # _LRScheduler.__init__ performs an initial step: lr = get_lr() at last_epoch 0
+    log = []
+    for _ in range(iterations):
+        for _ in range(2):
+            t_hat, w_hat = prop_forward(params, rays, num_samples, randomized)
+            out = nerf_forward(params, rays, t_hat, w_hat, randomized)
+            lp = Loss_prop(out[3].detach(), out[4].detach(), t_hat, w_hat)
+            opt.zero_grad()
+            lp.backward()
+            opt.step()
+            sched_step += 1
+            set_lr()
+        t_hat, w_hat = prop_forward(params, rays, num_samples, randomized)
+        rgb, _, _, _, w, s_vals = nerf_forward(params, rays, t_hat.detach(), w_hat.detach(), randomized)
+        ln, psnr = Loss_nerf(rgb, pixels)
+        ld = loss_dist(s_vals, w)
+        la = ln + dist_weight * ld
+        opt.zero_grad()
+        la.backward()
+        opt.step()
+        sched_step += 1
+        set_lr()
+        log.append([float(lp), float(ln), float(ld), float(la), float(psnr), lr_at(sched_step, **cfg)])
+    return {k: v.detach() for k, v in params.items()}, log
 
 
 def train_iteration_grads(sd, rays, pixels, num_samples, randomized=True, dist_weight=0.01):

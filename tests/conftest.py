@@ -10,6 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
+GOLDEN_R2 = os.path.join(ROOT, "tests", "golden", "reference_golden_r2.npz")
 
 
 def pytest_configure(config):
@@ -36,8 +37,8 @@ def pytest_collection_modifyitems(config, items):
 class Golden:
     """Access to the committed outputs of the literal reference (tests/golden/make_golden.py)."""
 
-    def __init__(self):
-        self._z = np.load(GOLDEN, allow_pickle=False)
+    def __init__(self, path=GOLDEN):
+        self._z = np.load(path, allow_pickle=False)
 
     def case(self, name, device="cpu"):
         out = {}
@@ -56,6 +57,12 @@ class Golden:
 @pytest.fixture(scope="session")
 def golden():
     return Golden()
+
+
+@pytest.fixture(scope="session")
+def golden2():
+    """Second fixture set (tests/golden/make_golden_r2.py): render_image, to8b, the train.py loop, rare branches."""
+    return Golden(GOLDEN_R2)
 
 
 def rays_from(case, device="cpu"):
