@@ -70,8 +70,10 @@ int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin
  *     t_vals[:, 1:] views (stride N+1) and separate contiguous t0, t1 (stride N) work.
  *   contract_mode: 0 = reference (global Frobenius norm, read from *norm_sq),
  *                  1 = per-point contraction (paper), 2 = no contraction.
- *   add_origins: 1 = means += origins after the contraction (para_rays, App. A2); 0 = not
- *     (conical_frustum_to_gaussian itself).
+ *   add_origins: bit 0 = means += origins after the contraction (para_rays, App. A2); clear = not
+ *     (conical_frustum_to_gaussian itself).  Bit 1 = use the original frustum formula of
+ *     parameterization.py:108-113 (stable=False) instead of the stable one; mip360_frustum_norm_sq always uses the
+ *     stable t_mean, so with bit 1 the caller supplies *norm_sq (mip360_sum_sq of the uncontracted means).
  *   vdir_enc [B,16] = mip360_viewdir_enc of the rays' view directions (needed for x_bf16 only).
  *   Outputs, each may be NULL: means [S,3], covs [S,3,3], enc [S,42] (fp32 IPE of the returned
  *     mean and cov), x_bf16 [S,64] = the MLP input row: 42 IPE features, 16 view-direction
@@ -88,6 +90,9 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
 /* intern/parameterization.py:31-62 (diag=False): d [B,3], t_mean/t_var/r_var [B,N] */
 int mip360_gaussian_to_xyz(const float* directions, const float* t_mean, const float* t_var, const float* r_var,
                            int B, int N, float* means, float* covs, mip360_stream_t stream);
+/* intern/parameterization.py:49-53 (diag=True): means [S,3] and the covariance diagonal cov_diag [S,3] */
+int mip360_gaussian_to_xyz_diag(const float* directions, const float* t_mean, const float* t_var, const float* r_var,
+                                int B, int N, float* means, float* cov_diag, mip360_stream_t stream);
 /* sum of squares of n floats accumulated into *out (double, caller-zeroed): torch.norm of parameterization.py:25 */
 int mip360_sum_sq(const float* x, long long n, double* out, mip360_stream_t stream);
 /* intern/parameterization.py:23-29: y = x if ||x||_F <= 1 else (2-1/n)(x/n), n^2 = *norm_sq */

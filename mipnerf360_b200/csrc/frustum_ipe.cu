@@ -28,6 +28,17 @@ __device__ __forceinline__ void split_sample(long long s, int N, unsigned long l
 }
 static inline unsigned long long div_magic(int N) { return N > 1 ? ~0ull / (unsigned long long)N + 1ull : 0ull; }
 
+// intern/parameterization.py:108-113: the original (numerically unstable) formula, kept for the callers that ask for it
+__device__ __forceinline__ void frustum_moments_unstable(float t0, float t1, float radius, float& t_mean, float& t_var,
+                                                         float& r_var) {
+  const float a2 = t0 * t0, b2 = t1 * t1;
+  const float a3 = a2 * t0, b3 = b2 * t1, a4 = a2 * a2, b4 = b2 * b2, a5 = a4 * t0, b5 = b4 * t1;  // torch: x**k
+  t_mean = (3.f * (b4 - a4)) / (4.f * (b3 - a3));
+  r_var = (radius * radius) * ((3.f / 20.f) * (b5 - a5) / (b3 - a3));
+  const float t_mosq = (3.f / 5.f) * (b5 - a5) / (b3 - a3);
+  t_var = t_mosq - t_mean * t_mean;
+}
+
 // intern/parameterization.py:101-107 (stable branch)
 __device__ __forceinline__ void frustum_moments(float t0, float t1, float radius, float& t_mean, float& t_var,
                                                 float& r_var) {
@@ -210,10 +221,11 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
   const float radius = radii[b];
 
   float t_mean, t_var, r_var, mean[3], cov[9];
-  frustum_moments(t0, t1, radius, t_mean, t_var, r_var);
+  if (add_origins & 2) frustum_moments_unstable(t0, t1, radius, t_mean, t_var, r_var);
+  else frustum_moments(t0, t1, radius, t_mean, t_var, r_var);
   lift_to_xyz(d, t_mean, t_var, r_var, mean, cov);
   contract_gaussian(mean, cov, contract_mode, n_global);
-  if (add_origins) {
+  if (add_origins & 1) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) mean[i] = mean[i] + origins[b * 3 + i];
   }
@@ -405,6 +417,24 @@ gaussian_to_xyz_kernel(const float* __restrict__ directions, const float* __rest
   for (int i = 0; i < 9; ++i) covs[s * 9 + i] = cov[i];
 }
 
+// intern/parameterization.py:49-53 (diag=True): the diagonal of the covariance only
+__global__ void __launch_bounds__(256)
+gaussian_to_xyz_diag_kernel(const float* __restrict__ directions, const float* __restrict__ t_mean,
+                            const float* __restrict__ t_var, const float* __restrict__ r_var, long long S, int N,
+                            float* __restrict__ means, float* __restrict__ cov_diag) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int b = (int)(s / N);
+  const float d[3] = {directions[b * 3], directions[b * 3 + 1], directions[b * 3 + 2]};
+  const float dmag = fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-10f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float dd = d[i] * d[i];
+    means[s * 3 + i] = d[i] * t_mean[s];
+    cov_diag[s * 3 + i] = t_var[s] * dd + r_var[s] * (1.f - dd / dmag);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ipe_kernel(const float* __restrict__ means, const float* __restrict__ covs, long long S, float* __restrict__ enc) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -518,7 +548,7 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
   MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "cast_ipe: bad sizes B=%d N=%d stride=%d", B, N, t_stride);
   MIP_REQUIRE(contract_mode >= 0 && contract_mode <= 2, "cast_ipe: contract_mode %d", contract_mode);
   MIP_REQUIRE(contract_mode != 0 || norm_sq, "cast_ipe: reference contraction needs norm_sq");
-  MIP_REQUIRE(!add_origins || origins, "cast_ipe: add_origins without origins");
+  MIP_REQUIRE(!(add_origins & 1) || origins, "cast_ipe: add_origins without origins");
   MIP_REQUIRE(!x_bf16 || vdir_enc, "cast_ipe: x_bf16 output needs vdir_enc [B,16]");
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
@@ -541,6 +571,17 @@ int mip360_gaussian_to_xyz(const float* directions, const float* t_mean, const f
   const long long S = (long long)B * N;
   gaussian_to_xyz_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(directions, t_mean, t_var, r_var, S, N,
                                                                                means, covs);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_gaussian_to_xyz_diag(const float* directions, const float* t_mean, const float* t_var, const float* r_var,
+                                int B, int N, float* means, float* cov_diag, mip360_stream_t stream) {
+  MIP_REQUIRE(B <= 0 || (directions && t_mean && t_var && r_var && means && cov_diag), "gaussian_to_xyz_diag: null pointer");
+  if (B <= 0) return MIP360_OK;
+  const long long S = (long long)B * N;
+  gaussian_to_xyz_diag_kernel<<<blocks_for(S, 256), 256, 0, (cudaStream_t)stream>>>(directions, t_mean, t_var, r_var, S,
+                                                                                    N, means, cov_diag);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -30,10 +30,8 @@ def contract(x):
 
 
 def gaussian_to_xyz(d, t_mean, t_var, r_var, diag=False):
-    """parameterization.py:31-62 (full covariance; the reference never uses diag=True on the hot path)."""
-    if diag:
-        raise NotImplementedError("diag=True is never reached by the reference hot path (ray.py:114,152)")
-    return ops.gaussian_to_xyz(d, t_mean, t_var, r_var)
+    """parameterization.py:31-62: full covariance [B,N,3,3], or its diagonal [B,N,3] with diag=True."""
+    return ops.gaussian_to_xyz(d, t_mean, t_var, r_var, diag=diag)
 
 
 def gaussian_contract(mean, cov):
@@ -41,17 +39,22 @@ def gaussian_contract(mean, cov):
     return ops.gaussian_contract(mean, cov)
 
 
+_DIAG_MSG = ("diag=True: the reference itself fails here — gaussian_contract multiplies the [B,N,3] diagonal by the "
+             "[B,N,3,3] Jacobians (parameterization.py:80-81, 'size of tensor a must match'); use gaussian_to_xyz(diag=True)")
+
+
 def conical_frustum_to_gaussian(d, t0, t1, base_radius, diag, stable=True):
-    """parameterization.py:85-117 (stable branch), contraction included."""
-    if diag or not stable:
-        raise NotImplementedError("only diag=False, stable=True is reached by the reference hot path")
-    out = ops.cast_ipe(None, None, d, base_radius, t0=t0, t1=t1, add_origins=False, want_means=True, want_covs=True)
+    """parameterization.py:85-117, contraction included; stable=False selects the original formula (:108-113)."""
+    if diag:
+        raise RuntimeError(_DIAG_MSG)
+    out = ops.cast_ipe(None, None, d, base_radius, t0=t0, t1=t1, add_origins=False, want_means=True, want_covs=True,
+                       stable=stable)
     return out["means"], out["covs"]
 
 
 def para_rays(t_vals, origins, directions, radii, diag=False):
     """parameterization.py:119-136: origins are added AFTER the contraction (App. A2)."""
     if diag:
-        raise NotImplementedError("diag=True is never reached by the reference hot path")
+        raise RuntimeError(_DIAG_MSG)
     out = ops.cast_ipe(t_vals, origins, directions, radii, want_means=True, want_covs=True)
     return out["means"], out["covs"]

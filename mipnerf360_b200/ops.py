@@ -61,9 +61,11 @@ def frustum_norm_sq(t0, t1, t_stride, directions, B, N, out=None):
 
 
 def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=None, contract_mode=CONTRACT_REFERENCE,
-             add_origins=True, norm_sq=None, want_means=False, want_covs=False, want_enc=False, want_x=False):
+             add_origins=True, norm_sq=None, want_means=False, want_covs=False, want_enc=False, want_x=False,
+             stable=True):
     """Fused cast -> Gaussian -> contract -> IPE (intern/parameterization.py:85-136, intern/encoding.py:33-61,
-    model.py:85-88).  Either t_vals [B,N+1] or separate t0, t1 [B,N].  Returns dict of requested outputs."""
+    model.py:85-88).  Either t_vals [B,N+1] or separate t0, t1 [B,N].  Returns dict of requested outputs.
+    stable=False selects the original frustum formula (parameterization.py:108-113)."""
     directions, radii = f32c(directions), f32c(radii)
     origins = f32c(origins) if origins is not None else None
     if t_vals is not None:
@@ -85,8 +87,15 @@ def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=N
                     covs=_empty((0, N, 3, 3), dev) if want_covs else None,
                     enc=_empty((0, N, 42), dev) if want_enc else None,
                     x=_empty((0, 64), dev, torch.bfloat16) if want_x else None, norm_sq=norm_sq)
+    flags = int(bool(add_origins)) | (0 if stable else 2)
     if contract_mode == CONTRACT_REFERENCE and norm_sq is None:
-        norm_sq = frustum_norm_sq(p0, p1, stride, directions, B, N)
+        if stable:
+            norm_sq = frustum_norm_sq(p0, p1, stride, directions, B, N)
+        else:  # the pre-pass kernel evaluates the stable t_mean: take the norm of the uncontracted means instead
+            raw = _empty((B, N, 3), dev)
+            call("mip360_cast_ipe", p0, p1, stride, None, ptr(directions), None, ptr(radii), None, B, N, CONTRACT_NONE, 2,
+                 ptr(raw), None, None, None)
+            norm_sq = sum_sq(raw)
     out = {}
     means = _empty((B, N, 3), dev) if want_means else None
     covs = _empty((B, N, 3, 3), dev) if want_covs else None
@@ -95,19 +104,21 @@ def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=N
     if want_x and vdir_enc is None:
         raise _lib.Mip360Error("cast_ipe: the bf16 MLP input needs vdir_enc")
     call("mip360_cast_ipe", p0, p1, stride, ptr(origins), ptr(directions), ptr(vdir_enc), ptr(radii), ptr(norm_sq), B, N,
-         int(contract_mode), int(bool(add_origins)), ptr(means), ptr(covs), ptr(enc), ptr(x))
+         int(contract_mode), flags, ptr(means), ptr(covs), ptr(enc), ptr(x))
     del keep
     out.update(means=means, covs=covs, enc=enc, x=x, norm_sq=norm_sq)
     return out
 
 
-def gaussian_to_xyz(d, t_mean, t_var, r_var):
-    """intern/parameterization.py:31-62 (diag=False)."""
+def gaussian_to_xyz(d, t_mean, t_var, r_var, diag=False):
+    """intern/parameterization.py:31-62: (means [B,N,3], covs [B,N,3,3]) or, with diag=True, the diagonal [B,N,3]."""
     d, t_mean, t_var, r_var = f32c(d), f32c(t_mean), f32c(t_var), f32c(r_var)
     check_cuda(d, t_mean, t_var, r_var)
     B, N = t_mean.shape
-    means, covs = _empty((B, N, 3), d), _empty((B, N, 3, 3), d)
-    call("mip360_gaussian_to_xyz", ptr(d), ptr(t_mean), ptr(t_var), ptr(r_var), B, N, ptr(means), ptr(covs))
+    means = _empty((B, N, 3), d)
+    covs = _empty((B, N, 3) if diag else (B, N, 3, 3), d)
+    call("mip360_gaussian_to_xyz_diag" if diag else "mip360_gaussian_to_xyz", ptr(d), ptr(t_mean), ptr(t_var), ptr(r_var),
+         B, N, ptr(means), ptr(covs))
     return means, covs
 
 

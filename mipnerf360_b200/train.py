@@ -231,7 +231,8 @@ class Trainer:
 
     # -- one reference iteration -------------------------------------------------------------------
     def prop_substep(self, rays):
-        """train.py:54-64: one proposal update.  Returns the loss (device scalar)."""
+        """train.py:54-64: one proposal update.  Returns the loss (device scalar; data parallel: this shard's share of
+        the global loss — the sum over ranks is the reference's value)."""
         m = self.model
         t_hat, w_hat = m.prop_net.forward(rays)
         with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
@@ -302,7 +303,10 @@ def check_sharded_equals_unsharded(device, rays_per_rank=512, num_samples=64, hi
     la_b, ps_b = solo.nerf_substep(rays, pixels)
     torch.cuda.synchronize()
     rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
-    out["loss_prop"] = rel(lp_a, lp_b)
+    # the returned proposal loss is the local shard's share of the global sum (already divided by the global batch)
+    lp_sum = lp_a.clone()
+    dist.all_reduce(lp_sum)
+    out["loss_prop"] = rel(lp_sum, lp_b)
     # loss_all = Loss_nerf (global, through the all-reduced squared error) + 0.01 * Loss_dist of the LOCAL shard:
     # the distortion term is a plain sum over rays (App. A9), so the global value is the sum of the shards' terms
     ln_a = 30 - ps_a
