@@ -295,6 +295,32 @@ int mip360_visualize_depth(const float* depth, const float* acc, const float* ra
 int mip360_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, int step, mip360_stream_t stream);
 
+/* One launch per net: [AdamW ->] refresh of the GEMM operands ("fused multi-tensor AdamW with the
+ * bf16 weight re-cast folded in").  Each table entry describes one layer of a packed MLP: up to two source blocks
+ * of fp32 rows (nn.Linear weights [rows, K] stacked into one padded [n_pad, k_pad] matrix — the NeRF heads
+ * final_density / final_color share one 64-row head), their biases, and the destinations: bf16 Wb [n_pad, k_pad], its
+ * transpose Wt [k_pad, n_pad] (may be NULL) and the padded fp32 bias [n_pad] (may be NULL).  tile_begin = first 32x32
+ * tile of the entry in the launch (entries sorted, total_tiles = sum of (n_pad/32)*(k_pad/32)).
+ * do_adam = 1: the sources lie inside the flat parameter buffer p; the element at p[i] is updated from g[i], m[i], v[i]
+ *   exactly as mip360_adamw does, then cast.  hyper_dev (device, may be NULL) = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}
+ *   overrides lr / step, so that a captured CUDA graph can be replayed with this step's values.  zero_grad = 1 clears g[i]
+ *   after use (the next backward pass accumulates into a zeroed buffer without a separate memset).
+ * do_adam = 0: cast only (after load_state_dict or an external optimiser changed the fp32 parameters). */
+typedef struct mip360_pack_entry {
+  const float* w_src[2]; /* fp32 [rows[i], K] row-major; w_src[1] NULL when rows[1] == 0 */
+  const float* b_src[2]; /* fp32 [rows[i]] */
+  int rows[2];
+  int K;
+  int n_pad, k_pad;      /* multiples of 32 */
+  int tile_begin;
+  uint16_t* Wb;
+  uint16_t* Wt;
+  float* bias;
+} mip360_pack_entry;
+int mip360_adamw_pack(const mip360_pack_entry* entries, int n_entries, int total_tiles, float* p, float* g, float* m,
+                      float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                      const float* hyper_dev, int do_adam, int zero_grad, mip360_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ SIGNATURES = {
     "mip360_depth_range": [P, P, c_longlong, c_double, c_float, c_float, c_int, c_int, P, P, P],
     "mip360_visualize_depth": [P, P, P, c_int, c_float, P, c_int, c_longlong, P, P, P],
     "mip360_adamw": [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P],
+    "mip360_adamw_pack": [P, c_int, c_int, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P, c_int, c_int, P],
 }
 _RESTYPES = {
     "mip360_last_error": c_char_p,
@@ -82,6 +83,12 @@ _RESTYPES = {
 class Layer(ctypes.Structure):
     """struct mip360_layer of include/mip360_b200.h."""
     _fields_ = [("W", c_void_p), ("Wt", c_void_p), ("bias", c_void_p), ("n_pad", c_int), ("k_pad", c_int), ("act", c_int)]
+
+
+class PackEntry(ctypes.Structure):
+    """struct mip360_pack_entry of include/mip360_b200.h."""
+    _fields_ = [("w_src", c_void_p * 2), ("b_src", c_void_p * 2), ("rows", c_int * 2), ("K", c_int), ("n_pad", c_int),
+                ("k_pad", c_int), ("tile_begin", c_int), ("Wb", c_void_p), ("Wt", c_void_p), ("bias", c_void_p)]
 
 
 _lib = None

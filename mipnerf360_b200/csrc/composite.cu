@@ -178,6 +178,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
       dist_raw = wt / a;
       const bool pass = !isnan(dist_raw) && !isinf(dist_raw) && dist_raw >= s.t[0] && dist_raw <= s.t[N];
       gd_scale = pass ? gd / a : 0.f;
+      if (!pass) dist_raw = 0.f;  // keeps 0 * (t_mid - NaN) out of G
     }
     float G[CP_MAXC], run = 0.f, excl_rev[CP_MAXC];
     // suffix sums of G_k w_k: walk the lane's chunk backwards
@@ -393,6 +394,7 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
       dist_raw = wt / a;
       const bool pass = !isnan(dist_raw) && !isinf(dist_raw) && dist_raw >= t_first && dist_raw <= t_last;
       gd_scale = pass ? gd / a : 0.f;
+      if (!pass) dist_raw = 0.f;  // keeps 0 * (t_mid - NaN) out of G
     }
     float run = 0.f, excl_rev[E];
 #pragma unroll

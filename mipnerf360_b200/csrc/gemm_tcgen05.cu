@@ -706,6 +706,86 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// One launch for a whole net: [AdamW on the flat fp32 parameters ->] bf16 operand copies of every layer (straight and
+// transposed, zero padded) and the padded fp32 bias vectors.  A block owns one 32 x 32 tile of one layer's padded weight
+// matrix (tile table in `entries`); the first tile column of a tile row also carries that row range of the bias.
+// AdamW arithmetic is adamw_kernel's, element for element.
+struct AdamHyper {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+};
+__device__ __forceinline__ float adam_update(float* p, float* g, float* m, float* v, long long i, const AdamHyper& h,
+                                             int zero_grad) {
+  const float gi = g[i];
+  const float pi = p[i] * (1.f - h.lr * h.wd);
+  const float mi = h.beta1 * m[i] + (1.f - h.beta1) * gi;
+  const float vi = h.beta2 * v[i] + (1.f - h.beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / h.bc2_sqrt + h.eps;
+  const float out = pi - (h.lr / h.bc1) * (mi / denom);
+  p[i] = out;
+  if (zero_grad) g[i] = 0.f;
+  return out;
+}
+
+__global__ void __launch_bounds__(256)
+adamw_pack_kernel(const mip360_pack_entry* __restrict__ entries, int n_entries, float* p_base, float* g_base,
+                  float* m_base, float* v_base, AdamHyper h, const float* __restrict__ hyper_dev, int do_adam,
+                  int zero_grad) {
+  __shared__ uint16_t tile[32][33];
+  __shared__ int s_entry;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && (int)blockIdx.x >= entries[e + 1].tile_begin) ++e;
+    s_entry = e;
+  }
+  __syncthreads();
+  const mip360_pack_entry E = entries[s_entry];
+  if (do_adam && hyper_dev) {  // learning rate and bias corrections of THIS step, written by the host before a graph replay
+    h.lr = hyper_dev[0];
+    h.bc1 = hyper_dev[1];
+    h.bc2_sqrt = hyper_dev[2];
+  }
+  const int local = (int)blockIdx.x - E.tile_begin;
+  const int tiles_k = E.k_pad / 32;
+  const int n0 = (local / tiles_k) * 32, k0 = (local % tiles_k) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rows_all = E.rows[0] + E.rows[1];
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    float val = 0.f;
+    if (n < rows_all && k < E.K) {
+      const float* src = n < E.rows[0] ? E.w_src[0] + (long long)n * E.K + k : E.w_src[1] + (long long)(n - E.rows[0]) * E.K + k;
+      if (do_adam) {
+        const long long i = src - p_base;
+        val = adam_update(p_base, g_base, m_base, v_base, i, h, zero_grad);
+      } else {
+        val = *src;
+      }
+    }
+    const __nv_bfloat16 b = __float2bfloat16_rn(val);
+    const uint16_t bits = *reinterpret_cast<const uint16_t*>(&b);
+    E.Wb[(long long)n * E.k_pad + k] = bits;
+    tile[r][tx] = bits;
+  }
+  __syncthreads();
+  if (E.Wt) {
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) E.Wt[(long long)(k0 + r) * E.n_pad + n0 + tx] = tile[tx][r];
+  }
+  if (k0 == 0 && ty == 0) {
+    const int n = n0 + tx;
+    float val = 0.f;
+    if (n < rows_all) {
+      const float* src = n < E.rows[0] ? E.b_src[0] + n : E.b_src[1] + (n - E.rows[0]);
+      if (do_adam) val = adam_update(p_base, g_base, m_base, v_base, src - p_base, h, zero_grad);
+      else val = *src;
+    }
+    if (E.bias) E.bias[n] = val;
+  }
+}
+
 // ---- host side: tensor maps ------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -895,6 +975,22 @@ int mip360_cast_weight(const float* W, int N, int K, int Npad, int Kpad, uint16_
   MIP_REQUIRE(N > 0 && K > 0 && Npad >= N && Kpad >= K, "cast_weight: bad shape");
   MIP_REQUIRE(Npad % 32 == 0 && Kpad % 32 == 0, "cast_weight: padded shape [%d, %d] must be multiples of 32", Npad, Kpad);
   cast_weight_kernel<<<dim3(Kpad / 32, Npad / 32), 256, 0, (cudaStream_t)stream>>>(W, N, K, Npad, Kpad, Wb, Wt);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
+int mip360_adamw_pack(const mip360_pack_entry* entries, int n_entries, int total_tiles, float* p, float* g, float* m,
+                      float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                      const float* hyper_dev, int do_adam, int zero_grad, mip360_stream_t stream) {
+  MIP_REQUIRE(entries && n_entries >= 1 && total_tiles >= 1, "adamw_pack: empty table");
+  MIP_REQUIRE(!do_adam || (p && g && m && v && (hyper_dev || step >= 1)), "adamw_pack: AdamW needs p, g, m, v and a step");
+  AdamHyper h{lr, beta1, beta2, eps, weight_decay, 1.f, 1.f};
+  if (do_adam && !hyper_dev) {
+    h.bc1 = 1.f - powf(beta1, (float)step);
+    h.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  }
+  adamw_pack_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(entries, n_entries, p, g, m, v, h, hyper_dev, do_adam,
+                                                                   zero_grad);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

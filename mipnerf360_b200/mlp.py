@@ -14,6 +14,10 @@ from . import _lib, ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID
 
 
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
 def pad_width(n):
     """Layer widths the tcgen05 tiles support: 64, 128 or a multiple of 256 (zero padded)."""
     if n <= 64:
@@ -28,14 +32,21 @@ class PackedMLP:
 
     trunk: list of (nn.Linear, act);  heads: list of nn.Linear whose rows are stacked into one padded
     [64, K] head; head_act is the activation applied to the head outputs (Sigmoid for nerf_net's
-    final_density / final_color, none for prop_net's last Linear)."""
+    final_density / final_color, none for prop_net's last Linear).
+
+    The bf16 copies (Wb, its transpose Wt, padded fp32 bias per layer) are allocated ONCE and refreshed in place by
+    one kernel launch (mip360_adamw_pack), so pointers baked into TMA descriptors, `struct mip360_layer` tables or
+    captured CUDA graphs stay valid across optimiser steps."""
 
     def __init__(self, trunk, heads, head_act):
         self.trunk = trunk
         self.heads = heads
         self.head_act = head_act
         self.n_valid = sum(h.out_features for h in heads)
-        self._key = None
+        if len(heads) > 2:
+            raise ValueError("at most two head Linear modules can share the padded head")
+        self._key = None        # (data_ptr, version) of every parameter at the last refresh
+        self._ptr_key = None    # data_ptr of every parameter the device table was built for
         self._packed = None
         # Opt-in (set by train.FlatAdamW): backward adds every dW/db straight into the preallocated .grad tensors
         # and returns None to autograd.  Off by default, so torch.autograd.grad(), tensor hooks and DDP see the
@@ -58,33 +69,71 @@ class PackedMLP:
             ps += [h.weight, h.bias]
         return ps
 
+    # -- buffers and device table --------------------------------------------------------------------------------
+    def _allocate(self, dev):
+        layers = []
+        k_pad = _pad64(self.trunk[0][0].in_features)  # the encoded input rows are 64 bf16 wide (58 features + zeros)
+        for lin, _ in self.trunk:
+            n_pad = pad_width(lin.out_features)
+            layers.append((torch.empty((n_pad, k_pad), device=dev, dtype=torch.bfloat16),
+                           torch.empty((k_pad, n_pad), device=dev, dtype=torch.bfloat16),
+                           torch.empty(n_pad, device=dev, dtype=torch.float32)))
+            k_pad = n_pad
+        head = (torch.empty((64, k_pad), device=dev, dtype=torch.bfloat16),
+                torch.empty((k_pad, 64), device=dev, dtype=torch.bfloat16),
+                torch.empty(64, device=dev, dtype=torch.float32))
+        self._packed = (layers, head)
+        acts = [a for _, a in self.trunk]
+        arr = (_lib.Layer * len(layers))()
+        for i, ((W_, Wt_, b_), a) in enumerate(zip(layers, acts)):
+            arr[i] = _lib.Layer(W_.data_ptr(), Wt_.data_ptr(), b_.data_ptr(), W_.shape[0], W_.shape[1], a)
+        Wb, Wt, bias = head
+        self._cstructs = (arr, _lib.Layer(Wb.data_ptr(), Wt.data_ptr(), bias.data_ptr(), 64, Wb.shape[1], self.head_act))
+
+    def _build_table(self):
+        """struct mip360_pack_entry per layer, uploaded to the device (rebuilt only when a parameter moved)."""
+        layers, head = self._packed
+        groups = [[lin] for lin, _ in self.trunk] + [list(self.heads)]
+        bufs = list(layers) + [head]
+        entries = (_lib.PackEntry * len(bufs))()
+        tile = 0
+        for i, (lins, (Wb, Wt, bias)) in enumerate(zip(groups, bufs)):
+            e = entries[i]
+            for j, lin in enumerate(lins):
+                if lin.weight.dtype != torch.float32 or not lin.weight.is_contiguous() or not lin.bias.is_contiguous():
+                    raise _lib.Mip360Error("PackedMLP: fp32 contiguous master weights expected")
+                e.w_src[j], e.b_src[j], e.rows[j] = lin.weight.data_ptr(), lin.bias.data_ptr(), lin.out_features
+            e.K = lins[0].in_features
+            e.n_pad, e.k_pad, e.tile_begin = Wb.shape[0], Wb.shape[1], tile
+            e.Wb, e.Wt, e.bias = Wb.data_ptr(), Wt.data_ptr(), bias.data_ptr()
+            tile += (Wb.shape[0] // 32) * (Wb.shape[1] // 32)
+        raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8)
+        self._table = raw.to(layers[0][0].device)
+        self._n_entries, self._n_tiles = len(bufs), tile
+
+    def table(self):
+        """(device pointer of the entry table, entries, tiles) for mip360_adamw_pack."""
+        ps = self.params()
+        if self._packed is None:
+            self._allocate(ps[0].device)
+        ptr_key = tuple(p.data_ptr() for p in ps)
+        if ptr_key != self._ptr_key:
+            self._build_table()
+            self._ptr_key = ptr_key
+        return self._table.data_ptr(), self._n_entries, self._n_tiles
+
+    def mark_fresh(self):
+        """The operands were just refreshed by a fused optimiser step (mip360_adamw_pack with do_adam = 1)."""
+        self._key = tuple((p.data_ptr(), p._version) for p in self.params())
+
     def packed(self):
         """(list of (Wb, Wt, bias), (Wb_head, Wt_head, bias_head)), refreshed when any parameter changed."""
         key = tuple((p.data_ptr(), p._version) for p in self.params())
         if key != self._key:
-            layers = []
-            k_pad = 64  # the encoded input rows are 64 bf16 wide (58 features + 6 zeros)
-            for lin, _ in self.trunk:
-                n_pad = pad_width(lin.out_features)
-                Wb, Wt = ops.cast_weight(lin.weight, n_pad=n_pad, k_pad=k_pad)
-                bias = torch.zeros(n_pad, device=Wb.device, dtype=torch.float32)
-                bias[: lin.out_features] = lin.bias.detach()
-                layers.append((Wb, Wt, bias))
-                k_pad = n_pad
-            Wh = torch.cat([h.weight.detach() for h in self.heads], 0)
-            bh = torch.cat([h.bias.detach() for h in self.heads], 0).float()
-            Wb, Wt = ops.cast_weight(Wh, n_pad=64, k_pad=k_pad)
-            bias = torch.zeros(64, device=Wh.device, dtype=torch.float32)
-            bias[: bh.numel()] = bh
-            self._packed = (layers, (Wb, Wt, bias))
+            tab, n_entries, n_tiles = self.table()
+            _lib.call("mip360_adamw_pack", tab, n_entries, n_tiles, None, None, None, None, 0.0, 0.0, 0.0, 0.0, 0.0, 0,
+                      None, 0, 0)
             self._key = key
-            # the same tables as `struct mip360_layer` arrays for the one-call C entry points
-            acts = [a for _, a in self.trunk]
-            arr = (_lib.Layer * len(layers))()
-            for i, ((W_, Wt_, b_), a) in enumerate(zip(layers, acts)):
-                arr[i] = _lib.Layer(W_.data_ptr(), Wt_.data_ptr(), b_.data_ptr(), W_.shape[0], W_.shape[1], a)
-            head = _lib.Layer(Wb.data_ptr(), Wt.data_ptr(), bias.data_ptr(), 64, Wb.shape[1], self.head_act)
-            self._cstructs = (arr, head)
         return self._packed
 
     def cstructs(self):

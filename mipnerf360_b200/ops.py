@@ -506,6 +506,15 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
          float(weight_decay), int(step))
 
 
+def adamw_pack_step(packed_mlp, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, hyper_dev=None, zero_grad=False):
+    """AdamW over the flat buffers of one net and, in the same launch, the refresh of its bf16 GEMM operands
+    (mlp.PackedMLP).  hyper_dev: device tensor [lr, 1 - beta1^step, sqrt(1 - beta2^step)] for graph replays."""
+    tab, n_entries, n_tiles = packed_mlp.table()
+    call("mip360_adamw_pack", tab, n_entries, n_tiles, ptr(p), ptr(g), ptr(m), ptr(v), float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), int(step), ptr(hyper_dev), 1, int(bool(zero_grad)))
+    packed_mlp.mark_fresh()
+
+
 # ------------------------------------------------------------------------------------------------
 # ray generation (SURVEY §8f rank 1)
 # ------------------------------------------------------------------------------------------------

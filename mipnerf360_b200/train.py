@@ -18,6 +18,7 @@ step computes what the unsharded reference step computes on the concatenated bat
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import torch
@@ -78,8 +79,10 @@ class FlatAdamW:
             packed = [m._packed for m in module.modules() if hasattr(m, "_packed")]
             for pk in packed:
                 pk.direct_grad = True
+            # one PackedMLP covering exactly the group's parameters: AdamW and the operand refresh are one launch
+            fused = len(packed) == 1 and {id(p) for p in packed[0].params()} == {id(p) for p in params}
             self.groups[name] = dict(params=params, flat=flat, grad=grad, m=torch.zeros_like(flat),
-                                     v=torch.zeros_like(flat), step=0, offsets=offsets, packed=packed)
+                                     v=torch.zeros_like(flat), step=0, offsets=offsets, packed=packed, fused=fused)
 
     def span(self, name, params):
         """[lo, hi) of the flat buffer covered by `params` (which must be adjacent in it)."""
@@ -92,12 +95,19 @@ class FlatAdamW:
         for name in (names or self.groups):
             self.groups[name]["grad"].zero_()
 
-    def step(self, names, lr=None):
+    def step(self, names, lr=None, hyper_dev=None, zero_grad=False):
+        """hyper_dev: device tensor [lr, 1 - beta1^step, sqrt(1 - beta2^step)] read by the kernel instead of the host
+        values (CUDA-graph replays).  zero_grad: clear the gradients in the same pass (fused path only)."""
         for name in names:
             g = self.groups[name]
             g["step"] += 1
-            ops.adamw_step(g["flat"], g["grad"], g["m"], g["v"], self.lr if lr is None else lr, self.betas[0],
-                           self.betas[1], self.eps, self.wd, g["step"])
+            lr_now = self.lr if lr is None else lr
+            if g["fused"]:
+                ops.adamw_pack_step(g["packed"][0], g["flat"], g["grad"], g["m"], g["v"], lr_now, self.betas[0],
+                                    self.betas[1], self.eps, self.wd, g["step"], hyper_dev=hyper_dev, zero_grad=zero_grad)
+                continue
+            ops.adamw_step(g["flat"], g["grad"], g["m"], g["v"], lr_now, self.betas[0], self.betas[1], self.eps, self.wd,
+                           g["step"])
             for pk in g["packed"]:
                 pk.invalidate()
 
@@ -150,13 +160,18 @@ class Trainer:
     overlap: bucket the gradient all-reduce per layer and overlap it with the rest of the backward pass."""
 
     def __init__(self, model, lr_init=2e-3, lr_final=2e-5, max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.1,
-                 weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=True):
+                 weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=True,
+                 fused_zero_grad=True):
         self.model = model
         self.sched = dict(lr_init=lr_init, lr_final=lr_final, max_steps=max_steps, lr_delay_steps=lr_delay_steps,
                           lr_delay_mult=lr_delay_mult)
         self.opt = FlatAdamW({"prop": model.prop_net, "nerf": model.nerf_net}, lr_init, weight_decay)
         self.dist_weight_decay = dist_weight_decay
         self.sched_step = 0
+        # the fused AdamW launch clears the gradient buffer it has just consumed, so the next sub-step of that net
+        # accumulates into zeros without a separate memset (set False to keep the gradients readable after a step)
+        self.fused_zero_grad = bool(fused_zero_grad)
+        self._grads_clean = {"prop": False, "nerf": False}
         self.group = group
         self.world = dist.get_world_size(group) if data_parallel and dist.is_available() and dist.is_initialized() else 1
         self.overlap = bool(overlap) and self.world > 1
@@ -164,9 +179,6 @@ class Trainer:
         if self.world > 1:
             if group is None:
                 self.group = dist.group.WORLD
-            # ray-sharded batch: the nets sum the batch-global contraction norm over the group (model._encode)
-            model.prop_net.batch_group = self.group
-            model.nerf_net.batch_group = self.group
             if self.overlap:
                 self.comm_stream = torch.cuda.Stream()
                 for name, net in (("prop", model.prop_net), ("nerf", model.nerf_net)):
@@ -205,13 +217,36 @@ class Trainer:
         else:
             dist.all_reduce(self.opt.groups[name]["grad"], op=dist.ReduceOp.SUM, group=self.group)
 
+    @contextlib.contextmanager
+    def _sharded_batch(self):
+        """Inside a training sub-step the nets see one shard of a data-parallel batch and sum the batch-global
+        contraction norm over the group (model._encode).  Outside (eval, render_image on any subset of the ranks)
+        model() stays free of collectives."""
+        nets = (self.model.prop_net, self.model.nerf_net)
+        prev = [n.batch_group for n in nets]
+        for n in nets:
+            n.batch_group = self.group if self.world > 1 else None
+        try:
+            yield
+        finally:
+            for n, g in zip(nets, prev):
+                n.batch_group = g
+
     # -- pieces ------------------------------------------------------------------------------------
     def _lr(self):
         return lr_at(self.sched_step, **self.sched)
 
+    def _zero_grad(self, name):
+        """optimizer.zero_grad() of train.py:61,79 for the net about to be back-propagated."""
+        if not self._grads_clean[name]:
+            self.opt.zero_grad([name])
+        self._grads_clean[name] = False
+
     def _optim(self, name):
         self._finish_grads(name)
-        self.opt.step([name], lr=self._lr())
+        zero = self.fused_zero_grad and self.opt.groups[name]["fused"]
+        self.opt.step([name], lr=self._lr(), zero_grad=zero)
+        self._grads_clean[name] = zero
         self.sched_step += 1  # scheduler.step() after every optimizer.step() (train.py:64,82; App. A11)
 
     def _loss_prop(self, t, w, t_hat, w_hat):
@@ -234,11 +269,12 @@ class Trainer:
         """train.py:54-64: one proposal update.  Returns the loss (device scalar; data parallel: this shard's share of
         the global loss — the sum over ranks is the reference's value)."""
         m = self.model
-        t_hat, w_hat = m.prop_net.forward(rays)
-        with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
-            _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
+        with self._sharded_batch():
+            t_hat, w_hat = m.prop_net.forward(rays)
+            with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
+                _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
         loss_prop = self._loss_prop(t, w, t_hat, w_hat)
-        self.opt.zero_grad(["prop"])
+        self._zero_grad("prop")
         loss_prop.backward()
         self._optim("prop")
         return loss_prop.detach()
@@ -247,13 +283,14 @@ class Trainer:
         """train.py:68-82: the NeRF update.  Returns (loss_all, psnr) (device scalars).  Data parallel: psnr and the
         photometric part of loss_all are those of the whole batch, the distortion part is the local shard's sum."""
         m = self.model
-        with torch.no_grad():
-            t_hat, w_hat = m.prop_net.forward(rays)
-        rgb, _, _, t, w, s = m.nerf_net.forward(rays, t_hat, w_hat)
+        with self._sharded_batch():
+            with torch.no_grad():
+                t_hat, w_hat = m.prop_net.forward(rays)
+            rgb, _, _, t, w, s = m.nerf_net.forward(rays, t_hat, w_hat)
         loss_nerf, psnr = self._loss_nerf(rgb, pixels)
         loss_dist = Loss_dist(s, w)
         loss_all = loss_nerf + self.dist_weight_decay * loss_dist
-        self.opt.zero_grad(["nerf"])
+        self._zero_grad("nerf")
         loss_all.backward()
         self._optim("nerf")
         return loss_all.detach(), psnr.detach()
@@ -293,7 +330,7 @@ def check_sharded_equals_unsharded(device, rays_per_rank=512, num_samples=64, hi
         torch.manual_seed(seed)
         models.append(mipNeRF360(randomized=False, num_samples=num_samples, hidden_proposal=hidden_proposal,
                                  hidden_nerf=hidden_nerf, device=device))
-    kw = dict(lr_init=1e-12, lr_final=1e-12)
+    kw = dict(lr_init=1e-12, lr_final=1e-12, fused_zero_grad=False)  # the gradients are compared after the step
     dp = Trainer(models[0], overlap=overlap, **kw)
     solo = Trainer(models[1], data_parallel=False, **kw)
     out = {}

@@ -44,11 +44,21 @@ def _worker(rank, world, port, q):
         res["dp_flat"] = check_sharded_equals_unsharded(dev, rays_per_rank=384, overlap=False, seed=1)
         res["dp_small"] = check_sharded_equals_unsharded(dev, rays_per_rank=96, num_samples=32, hidden_proposal=64,
                                                          hidden_nerf=128, seed=2)
-        # ray-partitioned render == single-GPU render with the same chunk boundaries
+        # ray-partitioned render == single-GPU render with the same chunk boundaries.  The model has been trained by a
+        # data-parallel Trainer first: rendering afterwards must stay free of collectives (the ranks below run
+        # different numbers of chunks — 4 and 3 for the 20x20 frame — which would deadlock a per-chunk all-reduce)
+        from mipnerf360_b200.synthetic import generic_rays
+        from mipnerf360_b200.train import Trainer
         torch.manual_seed(0)
         m = mipNeRF360(randomized=False, num_samples=32, hidden_proposal=64, hidden_nerf=128, device=dev)
+        tr = Trainer(m)
+        tr.step(*generic_rays(128, 50 + rank, device=dev))
+        flat = tr.opt.groups["nerf"]["flat"].clone()
+        dist.all_reduce(flat, op=dist.ReduceOp.MAX)
+        res["replicas_in_sync"] = bool(torch.equal(flat, tr.opt.groups["nerf"]["flat"]))  # same update on every rank
+        assert m.prop_net.batch_group is None and m.nerf_net.batch_group is None
         ok = True
-        for case in (llff_case(20, 24), garden_case(18, 26)):
+        for case in (llff_case(20, 24), garden_case(18, 26), garden_case(20, 20)):
             h, w = case["height"], case["width"]
             args = (case["c2w"], h, w, case["focal"], case["near"], case["far"], case["ndc"])
             out = render_frame(m, *args, chunks=64)                        # sharded, gathered on every rank
@@ -77,9 +87,14 @@ def test_two_ranks_sharded_equals_unsharded():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=900) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
+    try:
+        results = dict(q.get(timeout=600) for _ in range(world))
+        for p in procs:
+            p.join(timeout=120)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     for rank, res in results.items():
         assert "error" not in res, res["error"]
         for key in ("dp_overlap", "dp_flat", "dp_small"):
@@ -89,4 +104,5 @@ def test_two_ranks_sharded_equals_unsharded():
             assert r["loss_prop"] < 1e-4 and r["loss_all"] < 1e-4 and r["psnr"] < 1e-5, (rank, key, r)
             assert r["grad_prop"] < 2e-3 and r["grad_nerf"] < 2e-3, (rank, key, r)
         assert res["render_equal"], rank
+        assert res["replicas_in_sync"], rank
     print("two-rank check:", results[0])

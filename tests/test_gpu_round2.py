@@ -347,3 +347,65 @@ def test_flat_adamw_alone_keeps_the_bf16_operands_fresh():
     opt2.load_state_dict(sd)
     assert opt2.groups["nerf"]["step"] == 1 and opt2.groups["prop"]["step"] == 0
     assert torch.equal(opt2.groups["nerf"]["m"], opt.groups["nerf"]["m"])
+
+
+def test_fused_adamw_pack_equals_adamw_then_cast(ops):
+    """mip360_adamw_pack (AdamW + bf16 operand refresh, one launch per net) against mip360_adamw followed by the
+    cast-only launch, bit for bit; against torch.optim.AdamW to fp32 rounding; gradient clearing; device-side
+    hyper-parameters (the CUDA-graph path)."""
+    import math
+    from mipnerf360_b200.model import mipNeRF360
+    from mipnerf360_b200.train import FlatAdamW
+    dev = torch.device(DEV)
+    models, opts = [], []
+    for _ in range(3):
+        torch.manual_seed(4)
+        m = mipNeRF360(randomized=False, num_samples=32, hidden_proposal=64, hidden_nerf=128, device=dev)
+        models.append(m)
+        opts.append(FlatAdamW({"prop": m.prop_net, "nerf": m.nerf_net}, 3e-3, 1e-2))
+    ref_params = [p.detach().clone().requires_grad_(True) for p in models[0].parameters()]
+    ref_opt = torch.optim.AdamW(ref_params, lr=3e-3, weight_decay=1e-2)
+    for name in ("prop", "nerf"):
+        assert opts[0].groups[name]["fused"]
+        opts[1].groups[name]["fused"] = False          # two launches: adamw, then cast-only pack on the next packed()
+    hyper = torch.zeros(3, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    for step in range(1, 4):
+        for name in ("prop", "nerf"):
+            grad = torch.randn(opts[0].groups[name]["grad"].shape, device=dev, generator=g) * 1e-2
+            for o in opts:
+                o.groups[name]["grad"].copy_(grad)
+        for p, q in zip(ref_params, models[0].parameters()):
+            p.grad = q.grad.detach().clone()
+        opts[0].step(["prop", "nerf"], zero_grad=(step == 3))
+        opts[1].step(["prop", "nerf"])
+        hyper.copy_(torch.tensor([3e-3, 1 - 0.9 ** step, math.sqrt(1 - 0.999 ** step)]))
+        opts[2].step(["prop", "nerf"], lr=123.0, hyper_dev=hyper)  # the host lr must be ignored
+        ref_opt.step()
+        for name in ("prop", "nerf"):
+            assert torch.equal(opts[0].groups[name]["flat"], opts[1].groups[name]["flat"]), (step, name)
+            # bias corrections formed in fp64 on the host here, with powf on the host side of the library there
+            torch.testing.assert_close(opts[2].groups[name]["flat"], opts[0].groups[name]["flat"], rtol=1e-5, atol=1e-7)
+        for net in ("prop_net", "nerf_net"):
+            a, b = getattr(models[0], net)._packed.packed(), getattr(models[1], net)._packed.packed()
+            for (Wa, Wta, ba), (Wb_, Wtb, bb) in zip(a[0] + [a[1]], b[0] + [b[1]]):
+                assert torch.equal(Wa, Wb_) and torch.equal(Wta, Wtb) and torch.equal(ba, bb)
+                assert torch.equal(Wa.t().contiguous(), Wta)
+    for p, q in zip(ref_params, models[0].parameters()):
+        torch.testing.assert_close(q.detach(), p.detach(), rtol=2e-6, atol=2e-8)
+    assert float(opts[0].groups["nerf"]["grad"].abs().max()) == 0.0 and float(opts[1].groups["nerf"]["grad"].abs().max()) > 0
+    # the head rows: final_density in row 0, final_color in rows 1..3, zeros below; padded biases
+    pk = models[0].nerf_net._packed.packed()
+    Wh, _, bh = pk[1]
+    assert torch.equal(Wh[0, :128], models[0].nerf_net.final_density[0].weight.detach()[0].bfloat16())
+    assert torch.equal(Wh[1:4, :128], models[0].nerf_net.final_color[0].weight.detach().bfloat16())
+    assert float(Wh[4:].abs().max()) == 0.0 and float(bh[4:].abs().max()) == 0.0
+    assert torch.equal(bh[1:4], models[0].nerf_net.final_color[0].bias.detach())
+    # layer 0: 58 real input columns, 6 zero columns
+    W0 = pk[0][0][0]
+    assert W0.shape == (128, 64) and float(W0[:, 58:].abs().max()) == 0.0
+    # load_state_dict (in-place copy) is picked up by the version check
+    sd = {k: v + 0.25 for k, v in models[0].state_dict().items()}
+    models[0].load_state_dict(sd)
+    assert torch.equal(models[0].nerf_net._packed.packed()[0][1][0][:, :128],
+                       models[0].nerf_net.model[2].weight.detach().bfloat16())
