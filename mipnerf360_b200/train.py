@@ -24,7 +24,7 @@ import math
 import torch
 import torch.distributed as dist
 
-from mipnerf360_b200 import ops
+from mipnerf360_b200 import _lib, ops
 from mipnerf360_b200.intern.loss import Loss_dist, Loss_nerf, mse_to_psnr
 from mipnerf360_b200.intern.ray import Rays
 
@@ -157,11 +157,16 @@ class Trainer:
 
     group: torch.distributed process group of the data-parallel ranks (default: the world when initialised).
     data_parallel=False: ignore torch.distributed (every rank trains on its own, whole, batch).
-    overlap: bucket the gradient all-reduce per layer and overlap it with the rest of the backward pass."""
+    overlap: bucket the gradient all-reduce per layer and overlap it with the rest of the backward pass.
+    graph: capture the whole iteration (3 forward/backward/optimiser sub-steps, collectives included) in ONE CUDA
+        graph after `graph_warmup` eager iterations and replay it afterwards: ~330 kernel launches and the Python
+        between them become one launch.  The learning rate and Adam's bias corrections of the three optimiser steps are
+        read from a small device tensor the host refreshes before every replay; inputs are copied into static buffers.
+        A new batch shape triggers a new capture."""
 
     def __init__(self, model, lr_init=2e-3, lr_final=2e-5, max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.1,
                  weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=True,
-                 fused_zero_grad=True):
+                 fused_zero_grad=True, graph=False, graph_warmup=2):
         self.model = model
         self.sched = dict(lr_init=lr_init, lr_final=lr_final, max_steps=max_steps, lr_delay_steps=lr_delay_steps,
                           lr_delay_mult=lr_delay_mult)
@@ -172,6 +177,13 @@ class Trainer:
         # accumulates into zeros without a separate memset (set False to keep the gradients readable after a step)
         self.fused_zero_grad = bool(fused_zero_grad)
         self._grads_clean = {"prop": False, "nerf": False}
+        self.use_graph = bool(graph)
+        self.graph_warmup = int(graph_warmup)
+        self._graphs = {}       # batch size -> dict(graph, rays, pixels, out, launches)
+        self.replayed_launches = 0  # kernels of this library launched through graph replays (the C-side counter only sees captures)
+        self._eager_calls = 0
+        self._hyper = None      # device [3 sub-steps, 3] = lr, 1 - beta1^t, sqrt(1 - beta2^t), read by the captured AdamW
+        self._capture_substep = None
         self.group = group
         self.world = dist.get_world_size(group) if data_parallel and dist.is_available() and dist.is_initialized() else 1
         self.overlap = bool(overlap) and self.world > 1
@@ -245,7 +257,11 @@ class Trainer:
     def _optim(self, name):
         self._finish_grads(name)
         zero = self.fused_zero_grad and self.opt.groups[name]["fused"]
-        self.opt.step([name], lr=self._lr(), zero_grad=zero)
+        hyper = None
+        if self._capture_substep is not None:  # being captured: this step's scalars come from device memory at replay
+            hyper = self._hyper[self._capture_substep]
+            self._capture_substep += 1
+        self.opt.step([name], lr=self._lr(), zero_grad=zero, hyper_dev=hyper)
         self._grads_clean[name] = zero
         self.sched_step += 1  # scheduler.step() after every optimizer.step() (train.py:64,82; App. A11)
 
@@ -295,20 +311,85 @@ class Trainer:
         self._optim("nerf")
         return loss_all.detach(), psnr.detach()
 
-    def step(self, rays, pixels):
-        """train.py:52-82 on device-resident rays/pixels.  Returns (loss_prop, loss_all, psnr) as device scalars."""
+    def _step_eager(self, rays, pixels):
         loss_prop = None
         for _ in range(2):
             loss_prop = self.prop_substep(rays)
         loss_all, psnr = self.nerf_substep(rays, pixels)
         return loss_prop, loss_all, psnr
 
+    # -- whole-iteration CUDA graph -------------------------------------------------------------------------------
+    def _hyper_rows(self):
+        """[lr, 1 - beta1^t, sqrt(1 - beta2^t)] of the next three optimiser steps (prop, prop, nerf)."""
+        b1, b2 = self.opt.betas
+        rows, tp, tn = [], self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"]
+        for i, t in enumerate((tp + 1, tp + 2, tn + 1)):
+            rows.append([lr_at(self.sched_step + i, **self.sched), 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t)])
+        return torch.tensor(rows, dtype=torch.float32)
+
+    def _capture(self, rays, pixels):
+        if not all(g["fused"] for g in self.opt.groups.values()):
+            raise RuntimeError("graph=True needs the fused AdamW path (one PackedMLP per net)")
+        dev = pixels.device
+        if self._hyper is None:
+            self._hyper = torch.zeros((3, 3), device=dev, dtype=torch.float32)
+        st = dict(rays=Rays(*[r.detach().clone() for r in rays]), pixels=pixels.detach().clone(), graph=torch.cuda.CUDAGraph())
+        # host-side counters advance while capturing (no kernel runs); they are restored and advanced per replay instead
+        saved = (self.sched_step, self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"], dict(self._grads_clean))
+        self._capture_substep = 0
+        n0 = _lib.launch_count()
+        try:
+            with torch.cuda.graph(st["graph"], capture_error_mode="thread_local"):
+                lp, la, psnr = self._step_eager(st["rays"], st["pixels"])
+                st["out"] = torch.stack([lp, la, psnr])
+        finally:
+            self._capture_substep = None
+        st["launches"] = _lib.launch_count() - n0  # kernels of this library inside one replay
+        clean_after = dict(self._grads_clean)
+        self.sched_step, self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"], self._grads_clean = saved
+        if self._grads_clean != clean_after or not all(clean_after.values()):
+            # the captured iteration assumes the gradient buffers it finds are the ones it leaves behind (cleared by the
+            # fused AdamW); bring the buffers to that state once
+            self.opt.zero_grad()
+            self._grads_clean = clean_after
+        return st
+
+    def _step_graph(self, rays, pixels):
+        key = int(pixels.shape[0])
+        st = self._graphs.get(key)
+        if st is None:
+            if self._eager_calls < self.graph_warmup:
+                self._eager_calls += 1
+                return self._step_eager(rays, pixels)
+            st = self._graphs[key] = self._capture(rays, pixels)
+        for dst, src in zip(st["rays"], rays):
+            dst.copy_(src, non_blocking=True)
+        st["pixels"].copy_(pixels, non_blocking=True)
+        self._hyper.copy_(self._hyper_rows())  # 36 bytes, staged copy from pageable memory
+        st["graph"].replay()
+        self.replayed_launches += st["launches"]
+        self.sched_step += 3
+        self.opt.groups["prop"]["step"] += 2
+        self.opt.groups["nerf"]["step"] += 1
+        out = st["out"].clone()
+        return out[0], out[1], out[2]
+
+    def step(self, rays, pixels):
+        """train.py:52-82 on device-resident (or pinned host) rays/pixels.  Returns (loss_prop, loss_all, psnr) as
+        device scalars."""
+        if self.use_graph and _lib.PROFILE is None:  # instrumented runs (per-kernel events) stay eager
+            return self._step_graph(rays, pixels)
+        return self._step_eager(rays, pixels)
+
     def step_host(self, rays_host, pixels_host):
         """Same, from pinned host buffers: H2D copy of the batch, the iteration, D2H read of the losses."""
         dev = next(self.model.parameters()).device
-        rays = Rays(*[r.to(dev, non_blocking=True) for r in rays_host])
-        pixels = pixels_host.to(dev, non_blocking=True)
-        lp, la, psnr = self.step(rays, pixels)
+        if self.use_graph and int(pixels_host.shape[0]) in self._graphs and _lib.PROFILE is None:
+            lp, la, psnr = self.step(rays_host, pixels_host)  # straight into the graph's static input buffers
+        else:
+            rays = Rays(*[r.to(dev, non_blocking=True) for r in rays_host])
+            pixels = pixels_host.to(dev, non_blocking=True)
+            lp, la, psnr = self.step(rays, pixels)
         return torch.stack([lp, la, psnr]).cpu()
 
 
