@@ -483,7 +483,12 @@ def main():
                                              f"oracle port of the reference (fp32 torch CPU, {r['threads']} threads)"}
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them and drain the device before the communicator goes away, and do not
+        # let a stuck teardown keep a finished benchmark alive
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

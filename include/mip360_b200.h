@@ -56,6 +56,14 @@ int mip360_set_option(int key, int value);
  * ------------------------------------------------------------------------------------------ */
 int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand,
                          float* t_out, int B, int N, mip360_stream_t stream);
+/* The same with (a) the uniforms of ray.py:106 drawn inside the kernel when use_rng = 1 (Philox4x32-10 keyed by rng_seed;
+ * counter = (element b*(N+1)+i, rng_stream, *rng_epoch); u = (word >> 8) * 2^-24; rng_epoch is a device counter — may be
+ * NULL = 0 — so that a captured CUDA graph draws new numbers per replay), and (b) with norm_sq != NULL the squared
+ * Frobenius norm of the batch's uncontracted means (what mip360_frustum_norm_sq computes from t_out afterwards;
+ * parameterization.py:25,75) ACCUMULATED into *norm_sq in the same pass (directions [B,3] required). */
+int mip360_level0_sample(const float* near, const float* far, const float* s_lin, const float* t_rand, int use_rng,
+                         unsigned long long rng_seed, unsigned int rng_stream, const unsigned long long* rng_epoch,
+                         const float* directions, double* norm_sq, float* t_out, int B, int N, mip360_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  cast -> Gaussian -> contract -> IPE (+ view-direction encoding), fused
@@ -124,6 +132,15 @@ int mip360_resample_invert(const float* bins, const float* cdf, const float* u, 
                            int M, float* samples, int32_t* idx, mip360_stream_t stream);
 int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
                     int B, int N, float resample_padding, int blur, float* new_t, mip360_stream_t stream);
+/* The same with (a) the jitter of ray.py:33 drawn inside the kernel when use_rng = 1: jitter = u01 * jitter_scale with
+ * jitter_scale = 1/M - eps as torch's uniform_(0, 1/M - eps) scales it and u01 from the generator described at
+ * mip360_level0_sample (element index b*M + m), and (b) with norm_sq != NULL the squared Frobenius norm of the
+ * uncontracted means of the NEW knots accumulated into *norm_sq (what mip360_frustum_norm_sq computes from new_t). */
+int mip360_resample_sample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
+                           int use_rng, unsigned long long rng_seed, unsigned int rng_stream,
+                           const unsigned long long* rng_epoch, float jitter_scale, const float* directions,
+                           double* norm_sq, int B, int N, float resample_padding, int blur, float* new_t,
+                           mip360_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  volume compositing              intern/ray.py:155-191, model.py:59-78, model.py:184-185
@@ -145,6 +162,12 @@ int mip360_resample(const float* t_vals, const float* weights, const float* u_ba
 int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          float* comp_rgb, float* distance, float* acc, float* weights, mip360_stream_t stream);
+/* mip360_composite_fwd plus model.py:196 in the same pass: s_vals [B,N+1] = t_to_s(t_vals, near, far) and (optional)
+ * t_shift = t_vals + 1e-6 exactly as mip360_t_to_s produces them (near, far [B]). */
+int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
+                           int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
+                           float* comp_rgb, float* distance, float* acc, float* weights, const float* near,
+                           const float* far, float* s_vals, float* t_shift, mip360_stream_t stream);
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_dist, const float* g_w,
@@ -188,6 +211,10 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
 int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N,
                           float* b_out, mip360_stream_t stream);
 int mip360_bounds_reduce(const float* b, int B, int N, double* bound_total, mip360_stream_t stream);
+/* mip360_bounds_per_ray and mip360_bounds_reduce in one pass: b_out [B,N] (may be NULL when only the totals are
+ * wanted: the per-ray values then never touch HBM) and the column sums ACCUMULATED into bound_total [N] (may be NULL). */
+int mip360_bounds(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N, float* b_out,
+                  double* bound_total, mip360_stream_t stream);
 int mip360_interlevel_fwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,
                           int bound_mode, float batch_div, double* partials, float* loss, mip360_stream_t stream);
 int mip360_interlevel_bwd(const float* w_hat, const float* b_per_ray, const double* bound_total, int B, int N,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "mip360_sm_count": [],
     "mip360_set_option": [c_int, c_int],
     "mip360_level0_t_vals": [P, P, P, P, P, c_int, c_int, P],
+    "mip360_level0_sample": [P, P, P, P, c_int, ctypes.c_ulonglong, ctypes.c_uint, P, P, P, P, c_int, c_int, P],
     "mip360_frustum_norm_sq": [P, P, c_int, P, c_int, c_int, P, P],
     "mip360_cast_ipe": [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P],
     "mip360_gaussian_to_xyz": [P, P, P, P, c_int, c_int, P, P, P],
@@ -39,7 +40,10 @@ SIGNATURES = {
     "mip360_resample_cdf": [P, c_int, c_int, P, P],
     "mip360_resample_invert": [P, P, P, c_int, c_int, c_int, c_int, P, P, P],
     "mip360_resample": [P, P, P, P, c_int, c_int, c_float, c_int, P, P],
+    "mip360_resample_sample": [P, P, P, P, c_int, ctypes.c_ulonglong, ctypes.c_uint, P, c_float, P, P, c_int, c_int, c_float,
+                               c_int, P, P],
     "mip360_composite_fwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P],
+    "mip360_composite_fwd_s": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P, P],
     "mip360_composite_bwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P],
     "mip360_density_to_weight_fwd": [P, P, P, c_int, c_int, c_int, c_float, P, P],
     "mip360_density_to_weight_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
@@ -50,6 +54,7 @@ SIGNATURES = {
     "mip360_distortion_fwd": [P, P, c_int, c_int, P, P, P, P],
     "mip360_distortion_bwd": [P, P, c_int, c_int, P, P, P],
     "mip360_bounds_per_ray": [P, P, P, c_int, c_int, P, P],
+    "mip360_bounds": [P, P, P, c_int, c_int, P, P, P],
     "mip360_bounds_reduce": [P, c_int, c_int, P, P],
     "mip360_interlevel_fwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_interlevel_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],

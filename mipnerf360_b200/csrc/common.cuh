@@ -115,4 +115,40 @@ __device__ __forceinline__ float nan_to_num_f(float x, float nan_val = 0.f) {
 
 constexpr float G_EPS = 1e-6f;  // intern/parameterization.py:19
 
+// ---- counter-based random numbers (Philox4x32-10, Salmon et al. 2011) ------------------------------------------
+// The randomized draws of the reference (torch.rand of ray.py:106, uniform_ of ray.py:33) are generated inside the
+// kernels that consume them instead of being written to HBM and read back.  One uniform per (stream, element):
+//   counter = (element low, element high, stream id, epoch), key = 64-bit seed,
+//   u = (first output word >> 8) * 2^-24  in [0, 1).
+// `stream id` distinguishes the call sites of one iteration (host counter), `epoch` is read from device memory so that
+// a captured CUDA graph draws fresh numbers on every replay.  (The test suite carries a NumPy restatement, pinned to the
+// published Random123 known-answer vectors, that reproduces these uniforms bit for bit.)
+struct RngArgs {
+  unsigned long long seed;
+  const unsigned long long* epoch;  // device counter, may be null (epoch 0)
+  unsigned int stream_id;
+  int enabled;
+};
+__device__ __forceinline__ uint32_t philox_first_word(unsigned long long seed, unsigned long long element,
+                                                      uint32_t stream_id, uint32_t epoch) {
+  uint32_t c0 = (uint32_t)element, c1 = (uint32_t)(element >> 32), c2 = stream_id, c3 = epoch;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__device__ __forceinline__ float rng_uniform(const RngArgs& r, uint32_t epoch, unsigned long long element) {
+  return (float)(philox_first_word(r.seed, element, r.stream_id, epoch) >> 8) * 5.9604644775390625e-08f;
+}
+__device__ __forceinline__ uint32_t rng_epoch(const RngArgs& r) {
+  return r.epoch ? (uint32_t)(*r.epoch) : 0u;
+}
+
 }  // namespace mip360

@@ -79,12 +79,23 @@ __device__ __forceinline__ void stage_ray(CompositeSmem& s, const float* rgb_or_
   }
 }
 
+// intern/parameterization.py:5-8 with the eps shifts a single reference call observes (App. A4); see t_to_s_kernel
+__device__ __forceinline__ void t_to_s_one(float t, float near, float far, float& s, float& t_shift) {
+  const float t1 = t + G_EPS;
+  const float n1 = near + G_EPS;
+  const float f1 = far + G_EPS;
+  const float n2 = n1 + G_EPS;
+  s = (1.f / t1 - 1.f / n1) / (1.f / f1 - 1.f / n2);
+  t_shift = t1;
+}
+
 __global__ void __launch_bounds__(CP_WARPS * 32)
 composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                      const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
                      int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                      float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
-                     float* __restrict__ weights) {
+                     float* __restrict__ weights, const float* __restrict__ near, const float* __restrict__ far,
+                     float* __restrict__ s_vals, float* __restrict__ t_shift) {
   __shared__ CompositeSmem sm[CP_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CompositeSmem& s = sm[warp];
@@ -95,6 +106,15 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
     const float dx = dirs[b * 3], dy = dirs[b * 3 + 1], dz = dirs[b * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     __syncwarp();
+    if (s_vals) {  // model.py:196 fused: s_vals = t_to_s(t_vals, near, far) of the same knots
+      const float nr = near[b], fr = far[b];
+      for (int k = lane; k <= N; k += 32) {
+        float sv, ts;
+        t_to_s_one(s.t[k], nr, fr, sv, ts);
+        s_vals[(long long)b * (N + 1) + k] = sv;
+        if (t_shift) t_shift[(long long)b * (N + 1) + k] = ts;
+      }
+    }
     RayScan r;
     ray_weights(s, N, C, j0, dnorm, lane, r);
     float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
@@ -307,7 +327,8 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
                         const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int head_mode,
                         int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                         float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
-                        float* __restrict__ weights) {
+                        float* __restrict__ weights, const float* __restrict__ near, const float* __restrict__ far,
+                        float* __restrict__ s_vals, float* __restrict__ t_shift) {
   constexpr int N = E * RG_LANES;
   constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
@@ -317,9 +338,23 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
     rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
+    float nr = 0.f, fr = 0.f;
+    if (!WO && s_vals) { nr = __ldg(near + ray); fr = __ldg(far + ray); }
     rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
     if (weights && active) rg_store<E>(weights + ray * N + j0, r.w);
     if (weights_only) continue;
+    if (s_vals && active) {  // model.py:196 fused: the lane's knots j0 .. j0+E-1 (the last lane also writes knot N)
+      const int nk = E + (gl == RG_LANES - 1 ? 1 : 0);
+#pragma unroll
+      for (int i = 0; i <= E; ++i) {
+        if (i < nk) {
+          float sv, ts;
+          t_to_s_one(r.t[i], nr, fr, sv, ts);
+          s_vals[ray * (N + 1) + j0 + i] = sv;
+          if (t_shift) t_shift[ray * (N + 1) + j0 + i] = ts;
+        }
+      }
+    }
     float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
@@ -523,17 +558,26 @@ extern "C" {
 int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
                          float* distance, float* acc, float* weights, mip360_stream_t stream) {
+  return mip360_composite_fwd_s(rgb_or_raw, density, t_vals, dirs, B, N, head_mode, density_bias, rgb_padding, white_bkgd,
+                                comp_rgb, distance, acc, weights, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
+                           int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
+                           float* distance, float* acc, float* weights, const float* near, const float* far,
+                           float* s_vals, float* t_shift, mip360_stream_t stream) {
   MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs && comp_rgb && distance && acc), "composite_fwd: null pointer");
+  MIP_REQUIRE(B <= 0 || !s_vals || (near && far), "composite_fwd: s_vals needs near and far");
   MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_fwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_fwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
-                         rgb_padding, white_bkgd, comp_rgb, distance, acc, weights);
+                         rgb_padding, white_bkgd, comp_rgb, distance, acc, weights, near, far, s_vals, t_shift);
   else
     composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
-        distance, acc, weights);
+        distance, acc, weights, near, far, s_vals, t_shift);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -564,11 +608,12 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_fwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
-                         density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights);
+                         density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights,
+                         (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr);
   else
     composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
-        weights);
+        weights, nullptr, nullptr, nullptr, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

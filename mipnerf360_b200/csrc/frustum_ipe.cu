@@ -474,29 +474,61 @@ viewdir_enc_kernel(const float* __restrict__ viewdirs, int B, int min_deg, int m
   }
 }
 
-// intern/ray.py:100-111
+// intern/ray.py:100-111.  The stratified-jitter uniforms come from t_rand (given draw), else from the in-kernel
+// generator (rng.enabled), else the knots are deterministic.  With norm_sq != null the kernel also accumulates the
+// squared Frobenius norm the reference's contract() sees for these knots (parameterization.py:25,75; App. A1), so the
+// separate pre-pass over t_vals disappears: the thread of knot i owns interval [t_i, t_{i+1}].
 __global__ void __launch_bounds__(256)
 level0_t_kernel(const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ s_lin,
-                const float* __restrict__ t_rand, float* __restrict__ t_out, int B, int N) {
+                const float* __restrict__ t_rand, RngArgs rng, const float* __restrict__ directions,
+                double* __restrict__ norm_sq, float* __restrict__ t_out, int B, int N) {
   const int K = N + 1;
   const long long total = (long long)B * K;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int b = (int)(e / K), i = (int)(e - (long long)b * K);
-  const float gf = g_disp(far[b]), gn = g_disp(near[b]);
-  auto tv = [&](int k) {
-    const float s = s_lin[k];
-    return g_disp(s * gf + (1.f - s) * gn);
-  };
-  const float t = tv(i);
-  if (!t_rand) {
-    t_out[e] = t;
-    return;
+  const bool valid = e < total;
+  double contrib = 0.0;
+  if (valid) {
+    const int b = (int)(e / K), i = (int)(e - (long long)b * K);
+    const float gf = g_disp(far[b]), gn = g_disp(near[b]);
+    auto tv = [&](int k) {
+      const float s = s_lin[k];
+      return g_disp(s * gf + (1.f - s) * gn);
+    };
+    const bool randomized = t_rand != nullptr || rng.enabled;
+    const uint32_t epoch = rng.enabled ? rng_epoch(rng) : 0u;
+    // knot k of this ray with its jitter: mids = .5*(t[1:]+t[:-1]); upper = [mids, t[-1]]; lower = [t[0], mids]
+    auto knot = [&](int k, float tk, float t_prev, float t_next) {
+      if (!randomized) return tk;
+      const float upper = (k < N) ? 0.5f * (t_next + tk) : tk;
+      const float lower = (k > 0) ? 0.5f * (tk + t_prev) : tk;
+      const float u = t_rand ? t_rand[(long long)b * K + k] : rng_uniform(rng, epoch, (unsigned long long)b * K + k);
+      return lower + (upper - lower) * u;
+    };
+    const float t_im1 = i > 0 ? tv(i - 1) : 0.f, t_i = tv(i), t_ip1 = i < N ? tv(i + 1) : 0.f;
+    const float mine = knot(i, t_i, t_im1, t_ip1);
+    t_out[e] = mine;
+    if (norm_sq && i < N) {
+      const float t_ip2 = i + 1 < N ? tv(i + 2) : 0.f;
+      const float next = knot(i + 1, t_ip1, t_i, t_ip2);
+      // t_mean of parameterization.py:103 and |d t_mean|^2 formed like frustum_norm_sq_rg_kernel
+      const float mu = (mine + next) / 2.f, hw = (next - mine) / 2.f;
+      const float hw2 = hw * hw;
+      const float t_mean = mu + (2.f * mu * hw2) / (3.f * (mu * mu) + hw2);
+      const float m0 = directions[b * 3] * t_mean, m1 = directions[b * 3 + 1] * t_mean, m2 = directions[b * 3 + 2] * t_mean;
+      contrib = (double)(m0 * m0 + m1 * m1 + m2 * m2);
+    }
   }
-  // mids = .5*(t[1:]+t[:-1]); upper = [mids, t[-1]]; lower = [t[0], mids]
-  const float upper = (i < N) ? 0.5f * (tv(i + 1) + t) : t;
-  const float lower = (i > 0) ? 0.5f * (t + tv(i - 1)) : t;
-  t_out[e] = lower + (upper - lower) * t_rand[e];
+  if (norm_sq) {
+    contrib = warp_sum(contrib);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += sm[w];
+      atomicAdd(norm_sq, s);
+    }
+  }
 }
 
 static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -514,11 +546,21 @@ extern "C" {
 
 int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand, float* t_out,
                          int B, int N, mip360_stream_t stream) {
-  MIP_REQUIRE(B <= 0 || (near && far && s_lin && t_out), "level0_t_vals: null pointer");
-  MIP_REQUIRE(B >= 0 && N >= 1, "level0_t_vals: bad sizes B=%d N=%d", B, N);
+  return mip360_level0_sample(near, far, s_lin, t_rand, 0, 0ull, 0u, nullptr, nullptr, nullptr, t_out, B, N, stream);
+}
+
+int mip360_level0_sample(const float* near, const float* far, const float* s_lin, const float* t_rand, int use_rng,
+                         unsigned long long rng_seed, unsigned int rng_stream, const unsigned long long* rng_epoch,
+                         const float* directions, double* norm_sq, float* t_out, int B, int N, mip360_stream_t stream) {
+  MIP_REQUIRE(B <= 0 || (near && far && s_lin && t_out), "level0_sample: null pointer");
+  MIP_REQUIRE(B >= 0 && N >= 1, "level0_sample: bad sizes B=%d N=%d", B, N);
+  MIP_REQUIRE(!norm_sq || directions, "level0_sample: the norm needs the ray directions");
+  MIP_REQUIRE(!(t_rand && use_rng), "level0_sample: either a given draw or the in-kernel generator");
   if (B == 0) return MIP360_OK;
   const long long total = (long long)B * (N + 1);
-  level0_t_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, s_lin, t_rand, t_out, B, N);
+  RngArgs rng{rng_seed, rng_epoch, rng_stream, use_rng ? 1 : 0};
+  level0_t_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, s_lin, t_rand, rng, directions,
+                                                                          norm_sq, t_out, B, N);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

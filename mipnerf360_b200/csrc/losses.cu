@@ -125,11 +125,14 @@ struct __align__(16) BoundsSmem {
 // b[r,i] = sum_j w_j [t0_j <= R_i and t1_j >= L_i]  (closed intervals; distillation.py:25-29, App. B5)
 __global__ void __launch_bounds__(LS_WARPS * 32)
 bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
-              int B, int N, float* __restrict__ b_out) {
+              int B, int N, float* __restrict__ b_out, double* __restrict__ total) {
   __shared__ BoundsSmem sm[LS_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   BoundsSmem& s = sm[warp];
   const int C = (N + 31) >> 5, j0 = lane * C;
+  double col[LS_MAXC];  // column sums over this warp's rays (columns lane, lane + 32, ...)
+#pragma unroll
+  for (int c = 0; c < LS_MAXC; ++c) col[c] = 0.0;
   for (int b = blockIdx.x * LS_WARPS + warp; b < B; b += gridDim.x * LS_WARPS) {
     for (int k = lane; k <= N; k += 32) {
       s.tf[k] = t_fine[(long long)b * (N + 1) + k];
@@ -152,7 +155,10 @@ bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine
     }
     if (lane == 31) s.cumw[N] = incl;
     __syncwarp();
-    for (int i = lane; i < N; i += 32) {
+#pragma unroll
+    for (int ci = 0; ci < LS_MAXC; ++ci) {
+      const int i = lane + 32 * ci;
+      if (i >= N) break;
       const float L = s.tc[i], R = s.tc[i + 1];
       // lo = first j in [0,N) with t1_j = tf[j+1] >= L
       int lo = 0, hi = N;
@@ -170,9 +176,27 @@ bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine
       const int last = lo - 1;
       float v = 0.f;
       if (last >= first) v = fmaxf((float)(s.cumw[last + 1] - s.cumw[first]), 0.f);
-      b_out[(long long)b * N + i] = v;
+      if (b_out) b_out[(long long)b * N + i] = v;
+      col[ci] += (double)v;
     }
     __syncwarp();
+  }
+  if (total) {
+    // distillation.py:25-29 sums the bound of interval i over ALL rays (App. A6): block-level column sums, one atomic
+    // per column and block
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(sm);  // LS_WARPS x N doubles fit in the staging area
+#pragma unroll
+    for (int ci = 0; ci < LS_MAXC; ++ci) {
+      const int i = lane + 32 * ci;
+      if (i < N) red[warp * N + i] = col[ci];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += LS_WARPS * 32) {
+      double a = 0.0;
+      for (int w = 0; w < LS_WARPS; ++w) a += red[w * N + i];
+      atomicAdd(&total[i], a);
+    }
   }
 }
 
@@ -290,13 +314,16 @@ __device__ __forceinline__ int rg_skew_l(int i) {
 template <int E>
 __global__ void __launch_bounds__(RG_THREADS)
 bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
-                 int B, float* __restrict__ b_out) {
+                 int B, float* __restrict__ b_out, double* __restrict__ total) {
   constexpr int N = E * RG_LANES, K = N + 1, ROW = K + K / E + 2;
   __shared__ float s_tf[RG_RAYS_PER_BLOCK][ROW];
   __shared__ double s_cw[RG_RAYS_PER_BLOCK][ROW];
   const int gl = threadIdx.x & 7, g = threadIdx.x >> 3, j0 = gl * E;
   float* tfs = s_tf[g];
   double* cws = s_cw[g];
+  double col[E];  // column sums (columns gl + 8c) over the rays this lane group has seen
+#pragma unroll
+  for (int c = 0; c < E; ++c) col[c] = 0.0;
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
     const long long ray_raw = base + g;
     const bool active = ray_raw < B;
@@ -374,9 +401,26 @@ bounds_rg_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_f
       const int f = cntA[c], r = gl == RG_LANES - 1 ? b_l0 : b_dn;
       float v = 0.f;
       if (r - 1 >= f) v = fmaxf((float)(cws[rg_skew_l<E>(r)] - cws[rg_skew_l<E>(f)]), 0.f);
-      if (active) b_out[ray * N + gl + RG_LANES * c] = v;
+      if (active) {
+        if (b_out) b_out[ray * N + gl + RG_LANES * c] = v;
+        col[c] += (double)v;
+      }
     }
     __syncwarp();
+  }
+  if (total) {
+    // batch totals per coarse interval (App. A6): the 16 lane groups of the block fold their column sums through
+    // the (now idle) prefix-weight rows, one atomic per column and block
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < E; ++c) cws[gl + RG_LANES * c] = col[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += RG_THREADS) {
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < RG_RAYS_PER_BLOCK; ++q) a += s_cw[q][i];
+      atomicAdd(&total[i], a);
+    }
   }
 }
 
@@ -441,16 +485,24 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
 
 int mip360_bounds_per_ray(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N, float* b_out,
                           mip360_stream_t stream) {
-  MIP_REQUIRE(B <= 0 || (t_fine && w_fine && t_coarse && b_out), "bounds_per_ray: null pointer");
-  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds_per_ray: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  MIP_REQUIRE(B <= 0 || b_out, "bounds_per_ray: null pointer");
+  return mip360_bounds(t_fine, w_fine, t_coarse, B, N, b_out, nullptr, stream);
+}
+
+int mip360_bounds(const float* t_fine, const float* w_fine, const float* t_coarse, int B, int N, float* b_out,
+                  double* bound_total, mip360_stream_t stream) {
+  MIP_REQUIRE(B <= 0 || (t_fine && w_fine && t_coarse && (b_out || bound_total)), "bounds: null pointer");
+  MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "bounds: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   {
     cudaStream_t st = (cudaStream_t)stream;
     const bool rg = rg_supported_host(N);
-    if (rg && N == 32) bounds_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
-    else if (rg && N == 64) bounds_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
-    else if (rg && N == 128) bounds_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out);
-    else bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out);
+    // with totals every block ends in N atomics: cap the grid at a few blocks per SM
+    const int grid_rg = bound_total ? min(rg_grid(B), sm_count() * 8) : rg_grid(B);
+    if (rg && N == 32) bounds_rg_kernel<4><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
+    else if (rg && N == 64) bounds_rg_kernel<8><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
+    else if (rg && N == 128) bounds_rg_kernel<16><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
+    else bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out, bound_total);
   }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;

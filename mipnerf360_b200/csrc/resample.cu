@@ -76,6 +76,29 @@ __device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int 
   }
 }
 
+// |d t_mean|^2 of one interval, formed like frustum_norm_sq_rg_kernel (parameterization.py:103, App. A1)
+__device__ __forceinline__ double interval_norm_sq(float t0, float t1, float d0, float d1, float d2) {
+  const float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
+  const float hw2 = hw * hw;
+  const float t_mean = mu + (2.f * mu * hw2) / (3.f * (mu * mu) + hw2);
+  const float m0 = d0 * t_mean, m1 = d1 * t_mean, m2 = d2 * t_mean;
+  return (double)(m0 * m0 + m1 * m1 + m2 * m2);
+}
+// block sum of one double per thread, one atomicAdd per block
+template <int THREADS>
+__device__ __forceinline__ void block_atomic_add(double v, double* out) {
+  __shared__ double sm_part[THREADS / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += sm_part[i];
+    atomicAdd(out, s);
+  }
+}
+
 // ray.py:41-56: last knot with cdf <= u (upper_bound - 1), lerp inside the interval
 __device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int N, float u, int* idx_out) {
   int lo = 0, hi = N + 1;  // first k in [0, N+1) with cdf[k] > u
@@ -96,13 +119,15 @@ __device__ __forceinline__ float invert_one(const float* cdf, const float* bins,
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
-                const float* __restrict__ jitter, int B, int N, float padding, int blur,
-                float* __restrict__ new_t) {
+                const float* __restrict__ jitter, RngArgs rng, float jitter_scale, const float* __restrict__ directions,
+                double* __restrict__ norm_sq, int B, int N, float padding, int blur, float* __restrict__ new_t) {
   __shared__ ResampleSmem sm[RS_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ResampleSmem& s = sm[warp];
   const int K = N + 1;
   const float one_m_eps = 1.f - 1.1920928955078125e-07f;
+  const uint32_t epoch = rng.enabled ? rng_epoch(rng) : 0u;
+  double norm_acc = 0.0;
   for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
     const float* wrow = weights + (long long)b * N;
     const float* trow = t_vals + (long long)b * K;
@@ -123,14 +148,25 @@ resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weig
     __syncwarp();
     for (int m = lane; m < K; m += 32) {
       float u = u_base[m];
-      if (jitter) {
-        u = (u + u) + jitter[(long long)b * K + m];  // the doubled stratum offset is the reference's (App. A5)
+      if (jitter || rng.enabled) {
+        // ray.py:33: uniform_(0, 1/M - eps) — a given draw, or the in-kernel generator scaled the way torch scales it
+        const float jit = jitter ? jitter[(long long)b * K + m]
+                                 : rng_uniform(rng, epoch, (unsigned long long)b * K + m) * jitter_scale;
+        u = (u + u) + jit;  // the doubled stratum offset is the reference's (App. A5)
         u = fminf(u, one_m_eps);
       }
-      new_t[(long long)b * K + m] = invert_one(s.cdf, s.bins, N, u, nullptr);
+      const float x = invert_one(s.cdf, s.bins, N, u, nullptr);
+      new_t[(long long)b * K + m] = x;
+      if (norm_sq) s.wpad[m] = x;  // the padded weights are dead by now (N + 2 >= K slots)
     }
     __syncwarp();
+    if (norm_sq) {
+      const float d0 = directions[b * 3], d1 = directions[b * 3 + 1], d2 = directions[b * 3 + 2];
+      for (int j = lane; j < N; j += 32) norm_acc += interval_norm_sq(s.wpad[j], s.wpad[j + 1], d0, d1, d2);
+      __syncwarp();
+    }
   }
+  if (norm_sq) block_atomic_add<RS_WARPS * 32>(norm_acc, norm_sq);
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
@@ -205,7 +241,9 @@ __device__ __forceinline__ int rg_skew(int i) {
 template <int E>
 __global__ void __launch_bounds__(RG_THREADS)
 resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
-                   const float* __restrict__ jitter, int B, float padding, int blur, float* __restrict__ new_t) {
+                   const float* __restrict__ jitter, RngArgs rng, float jitter_scale,
+                   const float* __restrict__ directions, double* __restrict__ norm_sq, int B, float padding, int blur,
+                   float* __restrict__ new_t) {
   constexpr int N = E * RG_LANES, K = N + 1, ROW = K + K / E + 2;
   __shared__ float s_cdf[RG_RAYS_PER_BLOCK][ROW];
   __shared__ float s_bins[RG_RAYS_PER_BLOCK][ROW];
@@ -213,6 +251,9 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
   const float one_m_eps = 1.f - 1.1920928955078125e-07f;
   float* cdf = s_cdf[g];
   float* bins = s_bins[g];
+  const bool randomized = jitter != nullptr || rng.enabled;
+  const uint32_t epoch = rng.enabled ? rng_epoch(rng) : 0u;
+  double norm_acc = 0.0;
   for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
     const long long ray_raw = base + g;
     const bool active = ray_raw < B;
@@ -229,7 +270,14 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
     if (jitter) {
 #pragma unroll
       for (int c = 0; c <= E; ++c) jit[c] = __ldg(jitter + ray * K + ((c < E) ? gl + RG_LANES * c : N));
+    } else if (rng.enabled) {
+      // ray.py:33 drawn here instead of being read: uniform_(0, 1/M - eps) = u01 * (1/M - eps)
+#pragma unroll
+      for (int c = 0; c <= E; ++c)
+        jit[c] = rng_uniform(rng, epoch, (unsigned long long)ray * K + ((c < E) ? gl + RG_LANES * c : N)) * jitter_scale;
     }
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (norm_sq) { d0 = __ldg(directions + ray * 3); d1 = __ldg(directions + ray * 3 + 1); d2 = __ldg(directions + ray * 3 + 2); }
     if (blur) {
       float wl = __shfl_up_sync(FULL_MASK, w[E - 1], 1, RG_LANES);
       float wr = __shfl_down_sync(FULL_MASK, w[0], 1, RG_LANES);
@@ -292,7 +340,7 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
     for (int c = 0; c < S; ++c) {
       const int m = (c < E) ? gl + RG_LANES * c : N;
       u[c] = __ldg(u_base + m);
-      if (jitter) {
+      if (randomized) {
         u[c] = (u[c] + u[c]) + jit[c];  // the doubled stratum offset is the reference's (App. A5)
         u[c] = fminf(u[c], one_m_eps);
       }
@@ -326,10 +374,28 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
       const float den = c1 - c0, num = u[c] - c0;
       const float tt = den > 0.f ? fminf(fmaxf(__fdividef(num, den), 0.f), 1.f) : (num > 0.f ? 1.f : 0.f);
       const int m = (c < E) ? gl + RG_LANES * c : N;
-      if (active && (c < E || gl == 0)) new_t[ray * K + m] = b0 + tt * (b1 - b0);
+      const float x = b0 + tt * (b1 - b0);
+      if (active && (c < E || gl == 0)) new_t[ray * K + m] = x;
+      u[c] = x;  // kept for the norm below
     }
     __syncwarp();
+    if (norm_sq) {
+      // park the new knots in the (now dead) CDF row so that every lane can read interval ends t[m], t[m+1]
+#pragma unroll
+      for (int c = 0; c < S; ++c)
+        if (c < E || gl == 0) cdf[rg_skew<E>((c < E) ? gl + RG_LANES * c : N)] = u[c];
+      __syncwarp();
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < E; ++c) {
+          const int m = gl + RG_LANES * c;
+          norm_acc += interval_norm_sq(cdf[rg_skew<E>(m)], cdf[rg_skew<E>(m + 1)], d0, d1, d2);
+        }
+      }
+      __syncwarp();
+    }
   }
+  if (norm_sq) block_atomic_add<RG_THREADS>(norm_acc, norm_sq);
 }
 
 static inline int ray_grid(int B, int warps) {
@@ -377,22 +443,36 @@ int mip360_resample_invert(const float* bins, const float* cdf, const float* u, 
 
 int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter, int B, int N,
                     float resample_padding, int blur, float* new_t, mip360_stream_t stream) {
+  return mip360_resample_sample(t_vals, weights, u_base, jitter, 0, 0ull, 0u, nullptr, 0.f, nullptr, nullptr, B, N,
+                                resample_padding, blur, new_t, stream);
+}
+
+int mip360_resample_sample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
+                           int use_rng, unsigned long long rng_seed, unsigned int rng_stream,
+                           const unsigned long long* rng_epoch, float jitter_scale, const float* directions,
+                           double* norm_sq, int B, int N, float resample_padding, int blur, float* new_t,
+                           mip360_stream_t stream) {
   MIP_REQUIRE(B <= 0 || (t_vals && weights && u_base && new_t), "resample: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
+  MIP_REQUIRE(!norm_sq || directions, "resample: the norm needs the ray directions");
+  MIP_REQUIRE(!(jitter && use_rng), "resample: either a given draw or the in-kernel generator");
   if (B <= 0) return MIP360_OK;
   const bool rg = rg_supported_host(N);
+  const RngArgs rng{rng_seed, rng_epoch, rng_stream, use_rng ? 1 : 0};
+  cudaStream_t st = (cudaStream_t)stream;
   if (rg && N == 32)
-    resample_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
-                                                                              resample_padding, blur, new_t);
+    resample_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale, directions,
+                                                            norm_sq, B, resample_padding, blur, new_t);
   else if (rg && N == 64)
-    resample_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
-                                                                              resample_padding, blur, new_t);
+    resample_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale, directions,
+                                                            norm_sq, B, resample_padding, blur, new_t);
   else if (rg && N == 128)
-    resample_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, (cudaStream_t)stream>>>(t_vals, weights, u_base, jitter, B,
-                                                                               resample_padding, blur, new_t);
+    resample_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale,
+                                                             directions, norm_sq, B, resample_padding, blur, new_t);
   else
-    resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        t_vals, weights, u_base, jitter, B, N, resample_padding, blur, new_t);
+    resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale,
+                                                                     directions, norm_sq, B, N, resample_padding, blur,
+                                                                     new_t);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -6,8 +6,7 @@ from mipnerf360_b200 import ops
 
 def Loss_prop(t, w, t_hat, w_hat):
     """loss.py:6-21: bounds from the (detached) fine level, loss on the coarse weights."""
-    b = ops.bounds_per_ray(t, w, t_hat)
-    total = ops.bounds_total(b)
+    total = ops.bounds_batch_total(t, w, t_hat)
     return ops.interlevel_loss(w_hat, bound_total=total)
 
 

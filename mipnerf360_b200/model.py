@@ -8,6 +8,8 @@ running on the fused sm_100a path:
 The fp32 nn.Linear parameters are the master weights (checkpoints round-trip with the reference);
 MLP arithmetic is bf16 x bf16 -> fp32 (mlp.py).  Inputs are never mutated (App. A4).
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -25,7 +27,23 @@ def _kaiming_init(model):
             nn.init.kaiming_uniform_(module.weight)
 
 
-def _encode(rays, t_vals, viewdirs_encoding, contract_mode, batch_group=None):
+_VDIR_CACHE = {}
+
+
+def _viewdir_features(viewdirs_encoding, viewdirs):
+    """View-direction encoding of a ray batch, computed once per batch object: the six forwards of one training
+    iteration (train.py:54-71) and the two nets of one model(rays) call see the same `rays.viewdirs` tensor."""
+    key = (viewdirs_encoding.min_deg, viewdirs_encoding.max_deg)
+    hit = _VDIR_CACHE.get(key)
+    if hit is not None and hit[0]() is viewdirs and hit[1] == viewdirs._version and not torch.cuda.is_current_stream_capturing():
+        return hit[2]
+    enc = viewdirs_encoding(viewdirs)
+    if not torch.cuda.is_current_stream_capturing():  # tensors of a graph's private pool must not outlive a capture
+        _VDIR_CACHE[key] = (weakref.ref(viewdirs), viewdirs._version, enc)
+    return enc
+
+
+def _encode(rays, t_vals, viewdirs_encoding, contract_mode, batch_group=None, norm_sq=None):
     """cast -> Gaussian -> contract -> IPE ++ view-direction encoding, straight to bf16 MLP rows
     (model.py:82-88 / 169-176 without materialising means, covs or the [B,N,58] fp32 tensor).
 
@@ -33,17 +51,26 @@ def _encode(rays, t_vals, viewdirs_encoding, contract_mode, batch_group=None):
     group = the call is one ray shard of a data-parallel batch: the reference's batch-global contraction norm
     (App. A1) is summed over the group so that the sharded forward equals the unsharded one.  Only
     train.Trainer sets it; model(rays) / render_image never issue a collective."""
-    vd = viewdirs_encoding(rays.viewdirs)
+    vd = _viewdir_features(viewdirs_encoding, rays.viewdirs)
     if vd.shape[-1] != 16:
         raise ValueError("the fused encoder packs 16 view-direction features (viewdir_min_deg=0, viewdir_max_deg=4)")
-    norm_sq = None
+    # norm_sq: the batch's squared contraction norm, already accumulated by the kernel that produced t_vals
     if contract_mode == ops.CONTRACT_REFERENCE and batch_group is not None:
-        t = ops.f32c(t_vals)
-        B, N = t.shape[0], t.shape[1] - 1
-        norm_sq = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, ops.f32c(rays.directions), B, N)
+        if norm_sq is None:
+            t = ops.f32c(t_vals)
+            B, N = t.shape[0], t.shape[1] - 1
+            norm_sq = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, ops.f32c(rays.directions), B, N)
         dist.all_reduce(norm_sq, op=dist.ReduceOp.SUM, group=batch_group)
     return ops.cast_ipe(t_vals, rays.origins, rays.directions, rays.radii, vd, contract_mode=contract_mode,
                         norm_sq=norm_sq, want_x=True)["x"]
+
+
+def _norm_buffer(self, device):
+    """A zeroed fp64 scalar for the batch's squared contraction norm (App. A1), or None when the contraction mode does
+    not need it."""
+    if self.contract_mode != ops.CONTRACT_REFERENCE:
+        return None
+    return torch.zeros(1, device=device, dtype=torch.float64)
 
 
 class prop_net(nn.Module):
@@ -76,6 +103,8 @@ class prop_net(nn.Module):
         self.to(device)
         self._packed = _mlp.pack_prop(self.model)
 
+    _norm_buffer = _norm_buffer
+
     def density_to_weight(self, t_vals, density, dirs):
         """model.py:59-78."""
         return ops.density_to_weight(t_vals, density, dirs)
@@ -83,8 +112,10 @@ class prop_net(nn.Module):
     def forward(self, rays):
         """model.py:80-94 -> (t_vals [B,N+1], weights [B,N])."""
         B = rays.origins.shape[0]
-        t_vals = ops.level0_t_vals(rays.near, rays.far, self.num_samples, self.randomized)
-        x = _encode(rays, t_vals, self.viewdirs_encoding, self.contract_mode, self.batch_group)
+        norm_sq = self._norm_buffer(rays.near.device)
+        t_vals = ops.level0_t_vals(rays.near, rays.far, self.num_samples, self.randomized, directions=rays.directions,
+                                   norm_sq=norm_sq)  # sampling, its random draw and the contraction norm: one launch
+        x = _encode(rays, t_vals, self.viewdirs_encoding, self.contract_mode, self.batch_group, norm_sq)
         raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 1] logits
         weights = ops.density_to_weight(t_vals, raw.view(B, self.num_samples), rays.directions, raw_logits=True,
                                         density_bias=self.density_bias)
@@ -126,16 +157,21 @@ class nerf_net(nn.Module):
         self.to(device)
         self._packed = _mlp.pack_nerf(self.model, self.final_density, self.final_color)
 
+    _norm_buffer = _norm_buffer
+
     def forward(self, rays, t_vals, coarse_weights):
         """model.py:163-200 -> (rgb [B,3], dist [B], acc [B], t_vals [B,N+1], weights [B,N], s_vals [B,N+1])."""
         B = rays.origins.shape[0]
-        new_t = ops.resample(t_vals, coarse_weights, self.randomized, self.resample_padding)
+        norm_sq = self._norm_buffer(rays.near.device)
+        new_t = ops.resample(t_vals, coarse_weights, self.randomized, self.resample_padding, directions=rays.directions,
+                             norm_sq=norm_sq)
         N = new_t.shape[1] - 1
-        x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode, self.batch_group)
+        x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode, self.batch_group, norm_sq)
         raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 4] = (density head, colour head), post-sigmoid
-        comp_rgb, distance, acc, weights = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions,
-                                                               self.density_bias, self.rgb_padding, self.white_bkgd)
-        s_vals, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
+        # heads' activations, compositing and model.py:196's t_to_s in one launch
+        comp_rgb, distance, acc, weights, s_vals, t_shift = ops.composite_heads(
+            raw.view(B, N, 4), new_t, rays.directions, self.density_bias, self.rgb_padding, self.white_bkgd,
+            near=rays.near, far=rays.far)
         # model.py:193-196: stashed for the distillation / regularisation losses; the reference's t_vals comes
         # back shifted by +1e-6 because t_to_s -> g() adds eps in place (App. A4)
         self.fine_weights = weights

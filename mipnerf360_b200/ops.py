@@ -24,20 +24,67 @@ def _empty(shape, like, dtype=torch.float32):
 # ------------------------------------------------------------------------------------------------
 # K0 / K1
 # ------------------------------------------------------------------------------------------------
-def level0_t_vals(near, far, num_samples, randomized, t_rand=None):
-    """intern/ray.py:100-111.  near/far [B,1]; returns t_vals [B,N+1]."""
+# ------------------------------------------------------------------------------------------------
+# random draws: generated inside the consuming kernels (csrc/common.cuh), keyed by torch's seed
+# ------------------------------------------------------------------------------------------------
+class _Rng:
+    torch_seed = None
+    seed = 0
+    calls = 0
+    epochs = {}
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def rng_epoch(device):
+    """Device-resident replay counter of the in-kernel generator (one uint64 per device)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    ep = _Rng.epochs.get(key)
+    if ep is None:
+        ep = _Rng.epochs[key] = torch.zeros(1, device=torch.device("cuda", key), dtype=torch.int64)
+    return ep
+
+
+def rng_advance(device):
+    """Bump the replay counter: as the first node of a captured CUDA graph it makes every replay draw fresh numbers."""
+    rng_epoch(device).add_(1)
+
+
+def rng_next(device):
+    """(seed, stream id, epoch tensor) for the next randomized kernel call.  The key follows torch.manual_seed
+    (torch.initial_seed()), every call gets its own stream id, so runs are reproducible per seed and call order."""
+    ts = torch.initial_seed()
+    if ts != _Rng.torch_seed:
+        _Rng.torch_seed, _Rng.seed, _Rng.calls = ts, _splitmix64(ts & 0xFFFFFFFFFFFFFFFF), 0
+    _Rng.calls += 1
+    return _Rng.seed, _Rng.calls & 0xFFFFFFFF, rng_epoch(device)
+
+
+def level0_t_vals(near, far, num_samples, randomized, t_rand=None, directions=None, norm_sq=None, rng=None):
+    """intern/ray.py:100-111.  near/far [B,1]; returns t_vals [B,N+1].  randomized: the uniforms of ray.py:106 are the
+    given t_rand [B,N+1] or, by default, drawn inside the kernel (rng = (seed, stream id, epoch tensor) to pin them).
+    norm_sq (zeroed fp64 [1]) + directions: also accumulate the batch's squared contraction norm (App. A1) into it."""
     near, far = f32c(near), f32c(far)
     check_cuda(near, far)
     B = near.shape[0]
     s_lin = torch.linspace(0.0, 1, num_samples + 1, device=near.device)
-    if randomized and t_rand is None:
-        t_rand = torch.rand(B, num_samples + 1, device=near.device)
+    use_rng, seed, stream_id, epoch = 0, 0, 0, None
     if not randomized:
         t_rand = None
-    else:
+    elif t_rand is not None:
         t_rand = f32c(t_rand)
+    else:
+        seed, stream_id, epoch = rng if rng is not None else rng_next(near.device)
+        use_rng = 1
     t = _empty((B, num_samples + 1), near)
-    call("mip360_level0_t_vals", ptr(near), ptr(far), ptr(s_lin), ptr(t_rand), ptr(t), B, num_samples)
+    directions = f32c(directions) if norm_sq is not None else None
+    call("mip360_level0_sample", ptr(near), ptr(far), ptr(s_lin), ptr(t_rand), use_rng, seed, stream_id, ptr(epoch),
+         ptr(directions), ptr(norm_sq), ptr(t), B, num_samples)
     return t
 
 
@@ -206,25 +253,38 @@ def pdf_u_base(num_samples, randomized, device):
     return torch.linspace(0.0, 1.0 - EPS32, num_samples, device=device)
 
 
+def jitter_scale(num_samples):
+    """Upper end of uniform_(0, 1/M - eps) (intern/ray.py:33) as the fp32 value torch scales its [0,1) draw by."""
+    return float(torch.tensor(1 / num_samples - EPS32, dtype=torch.float32))
+
+
 def draw_jitter(B, num_samples, device):
     """intern/ray.py:33: uniform_(0, 1/M - eps)."""
     s = 1 / num_samples
     return torch.empty(B, num_samples, device=device).uniform_(to=(s - EPS32))
 
 
-def resample(t_vals, weights, randomized, resample_padding, jitter=None, blur=True):
-    """The no_grad block of intern/ray.py:136-149 (blur=True) or intern/ray.py:12-57 alone (blur=False)."""
+def resample(t_vals, weights, randomized, resample_padding, jitter=None, blur=True, directions=None, norm_sq=None,
+             rng=None):
+    """The no_grad block of intern/ray.py:136-149 (blur=True) or intern/ray.py:12-57 alone (blur=False).
+    randomized: the jitter of ray.py:33 is the given [B,N+1] draw or, by default, generated inside the kernel.
+    norm_sq (zeroed fp64 [1]) + directions: also accumulate the squared contraction norm of the NEW knots into it."""
     t_vals, weights = f32c(t_vals.detach()), f32c(weights.detach())
     check_cuda(t_vals, weights)
     B, N = weights.shape
     u_base = f32c(pdf_u_base(N + 1, randomized, t_vals.device))
-    if randomized:
-        jitter = draw_jitter(B, N + 1, t_vals.device) if jitter is None else f32c(jitter)
-    else:
+    use_rng, seed, stream_id, epoch = 0, 0, 0, None
+    if not randomized:
         jitter = None
+    elif jitter is not None:
+        jitter = f32c(jitter)
+    else:
+        seed, stream_id, epoch = rng if rng is not None else rng_next(t_vals.device)
+        use_rng = 1
     new_t = _empty((B, N + 1), t_vals)
-    call("mip360_resample", ptr(t_vals), ptr(weights), ptr(u_base), ptr(jitter), B, N, float(resample_padding),
-         int(bool(blur)), ptr(new_t))
+    directions = f32c(directions) if norm_sq is not None else None
+    call("mip360_resample_sample", ptr(t_vals), ptr(weights), ptr(u_base), ptr(jitter), use_rng, seed, stream_id, ptr(epoch),
+         jitter_scale(N + 1), ptr(directions), ptr(norm_sq), B, N, float(resample_padding), int(bool(blur)), ptr(new_t))
     return new_t
 
 
@@ -235,13 +295,15 @@ class _Composite(torch.autograd.Function):
     """intern/ray.py:155-191 (+ model.py:184-185 when head_mode=1)."""
 
     @staticmethod
-    def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd):
+    def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd, s_out=None):
         ctx.set_materialize_grads(False)  # unused outputs (distance, acc in training) arrive as None, not zeros
         B, N = t_vals.shape[0], t_vals.shape[1] - 1
         comp, dist, acc = _empty((B, 3), t_vals), _empty((B,), t_vals), _empty((B,), t_vals)
         w = _empty((B, N), t_vals)
-        call("mip360_composite_fwd", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
-             density_bias, rgb_padding, int(white_bkgd), ptr(comp), ptr(dist), ptr(acc), ptr(w))
+        near, far, s_vals, t_shift = s_out if s_out is not None else (None, None, None, None)
+        call("mip360_composite_fwd_s", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
+             density_bias, rgb_padding, int(white_bkgd), ptr(comp), ptr(dist), ptr(acc), ptr(w), ptr(near), ptr(far),
+             ptr(s_vals), ptr(t_shift))
         ctx.save_for_backward(rgb_or_raw, density, t_vals, dirs)
         ctx.cfg = (head_mode, density_bias, rgb_padding, int(white_bkgd))
         return comp, dist, acc, w
@@ -265,8 +327,8 @@ class _Composite(torch.autograd.Function):
              density_bias, rgb_padding, white, ptr(g_comp), ptr(g_acc), ptr(g_dist), ptr(g_w), ptr(g_rgb_in),
              ptr(g_density), ptr(g_raw))
         if head_mode == 1:
-            return g_raw, None, None, None, None, None, None, None
-        return g_rgb_in, g_density, None, None, None, None, None, None
+            return g_raw, None, None, None, None, None, None, None, None
+        return g_rgb_in, g_density, None, None, None, None, None, None, None
 
 
 def _no_grad_inputs(who, **tensors):
@@ -286,11 +348,20 @@ def composite(rgb, density, t_vals, dirs, white_bkgd):
     return _Composite.apply(rgb, density, t_vals, dirs, 0, 0.0, 0.0, bool(white_bkgd))
 
 
-def composite_heads(raw, t_vals, dirs, density_bias, rgb_padding, white_bkgd):
-    """model.py:184-186 fused: raw [B,N,4] = (density head, colour head) post-sigmoid outputs of the MLP."""
+def composite_heads(raw, t_vals, dirs, density_bias, rgb_padding, white_bkgd, near=None, far=None):
+    """model.py:184-186 fused: raw [B,N,4] = (density head, colour head) post-sigmoid outputs of the MLP.
+    With near / far the same launch also produces model.py:196's s_vals = t_to_s(t_vals, near, far) and the shifted
+    t_vals the reference returns (App. A4): -> (comp_rgb, distance, acc, weights, s_vals, t_shift)."""
     raw, t_vals, dirs = f32c(raw), f32c(t_vals), f32c(dirs)
     check_cuda(raw, t_vals, dirs)
-    return _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd))
+    if near is None:
+        return _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd))
+    near, far = f32c(near), f32c(far)
+    check_cuda(near, far)
+    s_vals, t_shift = torch.empty_like(t_vals), torch.empty_like(t_vals)
+    out = _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd),
+                           (near, far, s_vals, t_shift))
+    return out + (s_vals, t_shift)
 
 
 class _DensityToWeight(torch.autograd.Function):
@@ -399,6 +470,18 @@ def bounds_per_ray(t_fine, w_fine, t_coarse):
     b = _empty((B, N), w_fine)
     call("mip360_bounds_per_ray", ptr(t_fine), ptr(w_fine), ptr(t_coarse), B, N, ptr(b))
     return b
+
+
+def bounds_batch_total(t_fine, w_fine, t_coarse, out=None):
+    """Batch totals of the proposal bounds per coarse interval (intern/distillation.py:25-29, App. A6) straight from the
+    knots and fine weights: the per-ray values never touch HBM.  fp64 [N], accumulated into `out` if given."""
+    t_fine, w_fine, t_coarse = f32c(t_fine.detach()), f32c(w_fine.detach()), f32c(t_coarse.detach())
+    check_cuda(t_fine, w_fine, t_coarse)
+    B, N = w_fine.shape
+    if out is None:
+        out = torch.zeros(N, device=w_fine.device, dtype=torch.float64)
+    call("mip360_bounds", ptr(t_fine), ptr(w_fine), ptr(t_coarse), B, N, None, ptr(out))
+    return out
 
 
 def bounds_total(b_per_ray, out=None):

@@ -157,7 +157,11 @@ class Trainer:
 
     group: torch.distributed process group of the data-parallel ranks (default: the world when initialised).
     data_parallel=False: ignore torch.distributed (every rank trains on its own, whole, batch).
-    overlap: bucket the gradient all-reduce per layer and overlap it with the rest of the backward pass.
+    overlap: bucket the gradient all-reduce per layer (last layer first) and issue each bucket on a side stream as soon
+        as its wgrad has been enqueued, so that it overlaps the remaining dgrad / wgrad GEMMs.  Off by default: measured
+        on 8 B200 at 2048 rays per rank (profiles/r02_dp_breakdown_n8.json) the bucketed form costs 0.35 ms per
+        iteration against 0.18 ms for one flat 29.6 MB all-reduce after the backward pass — the persistent GEMM kernels
+        occupy every SM, so NCCL's copy kernels slow them down by more than the exposed transfer costs over NVSwitch.
     graph: capture the whole iteration (3 forward/backward/optimiser sub-steps, collectives included) in ONE CUDA
         graph after `graph_warmup` eager iterations and replay it afterwards: ~330 kernel launches and the Python
         between them become one launch.  The learning rate and Adam's bias corrections of the three optimiser steps are
@@ -165,7 +169,7 @@ class Trainer:
         A new batch shape triggers a new capture."""
 
     def __init__(self, model, lr_init=2e-3, lr_final=2e-5, max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.1,
-                 weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=True,
+                 weight_decay=1e-5, dist_weight_decay=0.01, group=None, data_parallel=True, overlap=False,
                  fused_zero_grad=True, graph=False, graph_warmup=2):
         self.model = model
         self.sched = dict(lr_init=lr_init, lr_final=lr_final, max_steps=max_steps, lr_delay_steps=lr_delay_steps,
@@ -177,6 +181,8 @@ class Trainer:
         # accumulates into zeros without a separate memset (set False to keep the gradients readable after a step)
         self.fused_zero_grad = bool(fused_zero_grad)
         self._grads_clean = {"prop": False, "nerf": False}
+        # timing experiments only (scripts/dp_breakdown.py): leave out a class of collectives — results are then wrong
+        self.debug_skip = set()  # subset of {"grads", "scalars"}
         self.use_graph = bool(graph)
         self.graph_warmup = int(graph_warmup)
         self._graphs = {}       # batch size -> dict(graph, rays, pixels, out, launches)
@@ -211,6 +217,8 @@ class Trainer:
         grad = self.opt.groups[name]["grad"]
 
         def hook(l):
+            if "grads" in self.debug_skip:
+                return
             lo, hi = spans[l]
             ready = torch.cuda.Event()
             ready.record()
@@ -221,7 +229,7 @@ class Trainer:
         return hook
 
     def _finish_grads(self, name):
-        if self.world == 1:
+        if self.world == 1 or "grads" in self.debug_skip:
             return
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
@@ -237,7 +245,7 @@ class Trainer:
         nets = (self.model.prop_net, self.model.nerf_net)
         prev = [n.batch_group for n in nets]
         for n in nets:
-            n.batch_group = self.group if self.world > 1 else None
+            n.batch_group = self.group if self.world > 1 and "scalars" not in self.debug_skip else None
         try:
             yield
         finally:
@@ -267,16 +275,16 @@ class Trainer:
 
     def _loss_prop(self, t, w, t_hat, w_hat):
         """loss.py:18-19 with the bound total and the batch size taken over ALL ranks."""
-        b = ops.bounds_per_ray(t, w, t_hat)
-        total = ops.bounds_total(b)
+        total = ops.bounds_batch_total(t, w, t_hat)  # per-ray bounds and their batch totals in one launch
         batch = float(w_hat.shape[0])
         if self.world > 1:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+            if "scalars" not in self.debug_skip:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
             batch *= self.world
         return ops.interlevel_loss(w_hat, bound_total=total, batch_div=batch)
 
     def _loss_nerf(self, rgb, pixels):
-        if self.world == 1:
+        if self.world == 1 or "scalars" in self.debug_skip:
             return Loss_nerf(rgb, pixels)
         return sharded_loss_nerf(rgb, pixels, self.world, self.group)
 
@@ -312,6 +320,7 @@ class Trainer:
         return loss_all.detach(), psnr.detach()
 
     def _step_eager(self, rays, pixels):
+        ops.rng_advance(pixels.device)  # first node of a captured iteration: every replay draws fresh numbers
         loss_prop = None
         for _ in range(2):
             loss_prop = self.prop_substep(rays)

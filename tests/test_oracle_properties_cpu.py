@@ -99,3 +99,19 @@ def test_contraction_jacobian_closed_form_matches_autograd(B, N, seed):
         for n in range(N):
             ref = torch.autograd.functional.jacobian(contract_point, x[b, n])
             torch.testing.assert_close(J[b, n], ref, rtol=1e-9, atol=1e-12)
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors: philox4x32 10)."""
+    from oracle import philox
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(x) for x in philox.philox4x32_10(ctr, key)) == out
+    u = philox.uniform(0x1234567890ABCDEF, 7, 3, (5, 9))
+    assert u.dtype.name == "float32" and u.shape == (5, 9) and (u >= 0).all() and (u < 1).all()
+    assert len(set(u.ravel().tolist())) == 45
+    assert not (philox.uniform(0x1234567890ABCDEF, 8, 3, (5, 9)) == u).any()   # another call site
+    assert not (philox.uniform(0x1234567890ABCDEF, 7, 4, (5, 9)) == u).any()   # another replay
