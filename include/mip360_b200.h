@@ -29,7 +29,7 @@ extern "C" {
 #define MIP360_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
 #define MIP360_ERR_UNSUPPORTED (-3) /* shape not supported by the tcgen05 path */
 
-#define MIP360_MAX_SAMPLES 128 /* N <= 128: one warp holds a ray (4 intervals per lane) */
+#define MIP360_MAX_SAMPLES 512 /* one warp holds a ray: <= 4 intervals per lane up to N = 128, <= 16 up to N = 512 */
 #define MIP360_ENC_DIM 42      /* 21 directions x {sin, cos}; intern/encoding.py:9-30 */
 #define MIP360_VDIR_DIM 16     /* 4 scales x {sin,cos} x {theta,phi}; intern/encoding.py:67 */
 #define MIP360_MLP_IN 58       /* model.py:39,127 */
@@ -93,6 +93,15 @@ int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float*
                     const float* vdir_enc, const float* radii, const double* norm_sq, int B, int N,
                     int contract_mode, int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16,
                     mip360_stream_t stream);
+
+/* mip360_cast_ipe for other view-direction degrees (ViewdirectionEncoding(min_deg, max_deg), encoding.py:63-90):
+ * vdir_enc [B, vd_dim] with vd_dim = 4 * (max_deg - min_deg), rows of x_cols = 64 (vd_dim <= 20) or 128 (vd_dim <= 84)
+ * bf16 columns: 42 IPE features, vd_dim view-direction features, zeros.  The MLP's first layer is packed to the same
+ * width (K padded to x_cols). */
+int mip360_cast_ipe_x(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
+                      const float* vdir_enc, int vd_dim, const float* radii, const double* norm_sq, int B, int N,
+                      int contract_mode, int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16,
+                      int x_cols, mip360_stream_t stream);
 
 /* stand-alone pieces of the same arithmetic, for the reference's unfused free functions */
 /* intern/parameterization.py:31-62 (diag=False): d [B,3], t_mean/t_var/r_var [B,N] */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mip360_level0_sample": [P, P, P, P, c_int, ctypes.c_ulonglong, ctypes.c_uint, P, P, P, P, c_int, c_int, P],
     "mip360_frustum_norm_sq": [P, P, c_int, P, c_int, c_int, P, P],
     "mip360_cast_ipe": [P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P],
+    "mip360_cast_ipe_x": [P, P, c_int, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, P, c_int, P],
     "mip360_gaussian_to_xyz": [P, P, P, P, c_int, c_int, P, P, P],
     "mip360_gaussian_to_xyz_diag": [P, P, P, P, c_int, c_int, P, P, P],
     "mip360_sum_sq": [P, c_longlong, P, P],

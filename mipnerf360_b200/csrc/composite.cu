@@ -7,8 +7,9 @@
 
 namespace mip360 {
 
-constexpr int CP_WARPS = 4;
-constexpr int CP_MAXC = (MIP360_MAX_SAMPLES + 31) / 32;
+constexpr int CP_WARPS = 2;  // generic kernels: 14 KB of staging per ray at the N = 512 limit
+// intervals per lane: 4 covers N <= 128, 16 the N <= 512 limit (template parameter MAXC of the generic kernels)
+constexpr int CP_MAXC_SMALL = 4, CP_MAXC_LARGE = (MIP360_MAX_SAMPLES + 31) / 32;
 
 struct __align__(16) CompositeSmem {
   float t[MIP360_MAX_SAMPLES + 1];
@@ -18,13 +19,15 @@ struct __align__(16) CompositeSmem {
   float gw[MIP360_MAX_SAMPLES];          // backward: total dL/dw
 };
 
+template <int CP_MAXC>
 struct RayScan {
   float dd[CP_MAXC], T[CP_MAXC], w[CP_MAXC], delta[CP_MAXC];
 };
 
 // weights of one ray: lane-chunked exclusive scan of sigma*delta
+template <int CP_MAXC>
 __device__ __forceinline__ void ray_weights(const CompositeSmem& s, int N, int C, int j0, float dnorm, int lane,
-                                            RayScan& r) {
+                                            RayScan<CP_MAXC>& r) {
   float run = 0.f;
   float excl[CP_MAXC];
 #pragma unroll
@@ -89,6 +92,7 @@ __device__ __forceinline__ void t_to_s_one(float t, float near, float far, float
   t_shift = t1;
 }
 
+template <int CP_MAXC>
 __global__ void __launch_bounds__(CP_WARPS * 32)
 composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                      const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
@@ -115,7 +119,7 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
         if (t_shift) t_shift[(long long)b * (N + 1) + k] = ts;
       }
     }
-    RayScan r;
+    RayScan<CP_MAXC> r;
     ray_weights(s, N, C, j0, dnorm, lane, r);
     float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
 #pragma unroll
@@ -154,6 +158,7 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
 
 // Backward.  G_j = g_w_j + g_rgb . c_j + g_acc' is the total gradient reaching w_j;
 //   dL/d(dd_j) = G_j T_j e^{-dd_j} - sum_{k>j} G_k w_k ,  dL/dsigma_j = dL/d(dd_j) delta_j.
+template <int CP_MAXC>
 __global__ void __launch_bounds__(CP_WARPS * 32)
 composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restrict__ density,
                      const float* __restrict__ t_vals, const float* __restrict__ dirs, int B, int N, int head_mode,
@@ -182,7 +187,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
       if (white_bkgd) ga -= (gr + gg + gb);
     }
     __syncwarp();
-    RayScan r;
+    RayScan<CP_MAXC> r;
     ray_weights(s, N, C, j0, dnorm, lane, r);
     // distance = clamp(nan_to_num(sum w t_mid / acc), t_0, t_N): d/dw_j = (t_mid_j - distance)/acc where the
     // quotient is finite and inside the clamp range (torch.clamp passes the gradient on the closed range)
@@ -549,6 +554,9 @@ static inline int ray_grid(int B, int warps) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// the generic kernel instantiation for N intervals per ray
+#define CP_GENERIC(kernel, N) ((N) <= 32 * CP_MAXC_SMALL ? kernel<CP_MAXC_SMALL> : kernel<CP_MAXC_LARGE>)
+
 }  // namespace mip360
 
 using namespace mip360;
@@ -575,7 +583,7 @@ int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const 
     launch_composite_fwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
                          rgb_padding, white_bkgd, comp_rgb, distance, acc, weights, near, far, s_vals, t_shift);
   else
-    composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    CP_GENERIC(composite_fwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
         distance, acc, weights, near, far, s_vals, t_shift);
   MIP_LAUNCH_CHECK();
@@ -594,7 +602,7 @@ int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const fl
     launch_composite_bwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
                          rgb_padding, white_bkgd, g_rgb, g_acc, g_dist, g_w, g_rgb_in, g_density, g_raw);
   else
-    composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    CP_GENERIC(composite_bwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
         g_dist, g_w, g_rgb_in, g_density, g_raw);
   MIP_LAUNCH_CHECK();
@@ -611,7 +619,7 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
                          density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights,
                          (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr);
   else
-    composite_fwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    CP_GENERIC(composite_fwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
         weights, nullptr, nullptr, nullptr, nullptr);
   MIP_LAUNCH_CHECK();
@@ -629,7 +637,7 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
                          density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, g_w,
                          (float*)nullptr, g_density, (float*)nullptr);
   else
-    composite_bwd_kernel<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    CP_GENERIC(composite_bwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr, g_w,
         nullptr, g_density, nullptr);
   MIP_LAUNCH_CHECK();

@@ -191,7 +191,8 @@ __device__ __forceinline__ void warp_store_rows(float* stage, const float* vals,
   __syncwarp();
 }
 
-template <bool FAST>
+// WIDE: bf16 rows of 128 columns (more than 22 view-direction features); the default is 64
+template <bool FAST, bool WIDE = false>
 __global__ void __launch_bounds__(K1_THREADS)
 cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, int t_stride,
                 const float* __restrict__ origins, const float* __restrict__ directions,
@@ -199,7 +200,7 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
                 const double* __restrict__ norm_sq, long long S, int N, unsigned long long magic, int contract_mode,
                 int add_origins,
                 float* __restrict__ means_out, float* __restrict__ covs_out, float* __restrict__ enc_out,
-                uint16_t* __restrict__ x_out) {
+                uint16_t* __restrict__ x_out, int vd_dim, int x_cols) {
   __shared__ __align__(16) float stage_all[(K1_THREADS / 32) * K1_STAGE_FLOATS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stage = stage_all + warp * K1_STAGE_FLOATS;
@@ -257,32 +258,49 @@ cast_ipe_kernel(const float* __restrict__ t0p, const float* __restrict__ t1p, in
     }
   }
   if (x_out) {
-    // bf16 rows of 64: [0,42) IPE, [42,58) view-direction encoding of the ray, [58,64) zeros.
-    // Each lane converts its own row to 8 x 16-byte chunks, stored XOR-swizzled, then the warp writes
-    // its 4 KB (32 rows x 128 B, contiguous in global memory) with 16-byte coalesced stores.
-    const float4* vd4 = reinterpret_cast<const float4*>(vdir_enc + (long long)b * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v = vd4[q];
-      packed[21 + 2 * q] = pack_bf16x2(v.x, v.y);
-      packed[22 + 2 * q] = pack_bf16x2(v.z, v.w);
-    }
-    packed[29] = packed[30] = packed[31] = 0u;
-    __syncwarp();  // everyone is done reading the fp32 staging rows
+    // bf16 rows of x_cols (64, or 128 when more than 22 view-direction features are configured): [0,42) IPE,
+    // [42,42+vd_dim) view-direction encoding of the ray, zeros up to x_cols.  Per 64-column half: each lane
+    // converts its own half-row to 8 x 16-byte chunks, stored XOR-swizzled, then the warp writes the 32 half-rows
+    // (128 B each, whole lines) with 16-byte coalesced stores.
+    const float* vd = vdir_enc + (long long)b * vd_dim;
+    auto vdv = [&](int k) { return k < vd_dim ? __ldg(vd + k) : 0.f; };
     uint4* stage4 = reinterpret_cast<uint4*>(stage);
+    constexpr int chunks_per_row = WIDE ? 16 : 8;  // 16-byte chunks per bf16 row
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      stage4[lane * 8 + (c ^ (lane & 7))] =
-          make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-    __syncwarp();
-    uint4* g4 = reinterpret_cast<uint4*>(x_out + warp_s0 * 64);
-    const int total = rows_valid * 8;
+    for (int h = 0; h < (WIDE ? 2 : 1); ++h) {
+      if (h == 0) {
+        if (vd_dim == 16) {  // the default (viewdir degrees 0..4): four 16-byte loads
+          const float4* vd4 = reinterpret_cast<const float4*>(vd);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int q = it * 32 + lane;
-      if (q < total) {
-        const int r = q >> 3, c = q & 7;
-        g4[q] = stage4[r * 8 + (c ^ (r & 7))];
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = vd4[q];
+            packed[21 + 2 * q] = pack_bf16x2(v.x, v.y);
+            packed[22 + 2 * q] = pack_bf16x2(v.z, v.w);
+          }
+          packed[29] = packed[30] = packed[31] = 0u;
+        } else {
+#pragma unroll
+          for (int p = 21; p < 32; ++p) packed[p] = pack_bf16x2(vdv(2 * (p - 21)), vdv(2 * (p - 21) + 1));
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) packed[p] = pack_bf16x2(vdv(22 + 64 * (h - 1) + 2 * p), vdv(23 + 64 * (h - 1) + 2 * p));
+      }
+      __syncwarp();  // everyone is done reading the staging rows (fp32 features / the previous half)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        stage4[lane * 8 + (c ^ (lane & 7))] =
+            make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+      __syncwarp();
+      uint4* g4 = reinterpret_cast<uint4*>(x_out) + warp_s0 * chunks_per_row + 8 * h;
+      const int total = rows_valid * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int q = it * 32 + lane;
+        if (q < total) {
+          const int r = q >> 3, c = q & 7;
+          g4[(long long)r * chunks_per_row + c] = stage4[r * 8 + (c ^ (r & 7))];
+        }
       }
     }
   }
@@ -586,22 +604,36 @@ int mip360_frustum_norm_sq(const float* t0, const float* t1, int t_stride, const
 int mip360_cast_ipe(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
                     const float* vdir_enc, const float* radii, const double* norm_sq, int B, int N, int contract_mode,
                     int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16, mip360_stream_t stream) {
+  return mip360_cast_ipe_x(t0, t1, t_stride, origins, directions, vdir_enc, MIP360_VDIR_DIM, radii, norm_sq, B, N,
+                           contract_mode, add_origins, means, covs, enc, x_bf16, MIP360_MLP_IN_PAD, stream);
+}
+
+int mip360_cast_ipe_x(const float* t0, const float* t1, int t_stride, const float* origins, const float* directions,
+                      const float* vdir_enc, int vd_dim, const float* radii, const double* norm_sq, int B, int N,
+                      int contract_mode, int add_origins, float* means, float* covs, float* enc, uint16_t* x_bf16,
+                      int x_cols, mip360_stream_t stream) {
+  MIP_REQUIRE(!x_bf16 || (vd_dim >= 0 && vd_dim % 4 == 0 && (x_cols == 64 || x_cols == 128) && 42 + vd_dim <= x_cols),
+              "cast_ipe: %d view-direction features do not fit bf16 rows of %d columns (64 or 128)", vd_dim, x_cols);
   MIP_REQUIRE(B <= 0 || (t0 && t1 && directions && radii), "cast_ipe: null pointer");
   MIP_REQUIRE(B >= 0 && N >= 1 && t_stride >= N, "cast_ipe: bad sizes B=%d N=%d stride=%d", B, N, t_stride);
   MIP_REQUIRE(contract_mode >= 0 && contract_mode <= 2, "cast_ipe: contract_mode %d", contract_mode);
   MIP_REQUIRE(contract_mode != 0 || norm_sq, "cast_ipe: reference contraction needs norm_sq");
   MIP_REQUIRE(!(add_origins & 1) || origins, "cast_ipe: add_origins without origins");
-  MIP_REQUIRE(!x_bf16 || vdir_enc, "cast_ipe: x_bf16 output needs vdir_enc [B,16]");
+  MIP_REQUIRE(!x_bf16 || vdir_enc || vd_dim == 0, "cast_ipe: x_bf16 output needs vdir_enc [B,vd_dim]");
   if (B == 0) return MIP360_OK;
   const long long S = (long long)B * N;
-  if (x_bf16 && !means && !covs && !enc)
+  if (x_bf16 && x_cols == 128)
+    cast_ipe_kernel<false, true><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
+        t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, div_magic(N), contract_mode, add_origins,
+        means, covs, enc, x_bf16, vd_dim, x_cols);
+  else if (x_bf16 && !means && !covs && !enc)
     cast_ipe_kernel<true><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
         t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, div_magic(N), contract_mode, add_origins,
-        means, covs, enc, x_bf16);
+        means, covs, enc, x_bf16, vd_dim, x_cols);
   else
     cast_ipe_kernel<false><<<blocks_for(S, K1_THREADS), K1_THREADS, 0, (cudaStream_t)stream>>>(
         t0, t1, t_stride, origins, directions, vdir_enc, radii, norm_sq, S, N, div_magic(N), contract_mode, add_origins,
-        means, covs, enc, x_bf16);
+        means, covs, enc, x_bf16, vd_dim, x_cols);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

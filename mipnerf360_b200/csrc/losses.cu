@@ -8,7 +8,9 @@
 namespace mip360 {
 
 constexpr int LS_WARPS = 4;
-constexpr int LS_MAXC = (MIP360_MAX_SAMPLES + 31) / 32;
+// intervals per lane of the generic kernels: 4 covers N <= 128, 16 the N <= 512 limit (template parameter LS_MAXC)
+constexpr int LS_MAXC_SMALL = 4, LS_MAXC_LARGE = (MIP360_MAX_SAMPLES + 31) / 32;
+#define LS_GENERIC(N, ...) ((N) <= 32 * LS_MAXC_SMALL ? __VA_ARGS__ LS_MAXC_SMALL> : __VA_ARGS__ LS_MAXC_LARGE>)
 constexpr int LS_MAX_PARTIALS = 4096;
 
 __device__ __forceinline__ double warp_scan_incl_d(double v, int lane) {
@@ -26,7 +28,7 @@ struct __align__(16) DistSmem {
 };
 
 // per-ray: 2 sum_i w_i (m_i W_<i - (wm)_<i) + 1/3 sum_i w_i^2 ds_i   (m sorted, App. A9)
-template <bool BWD>
+template <bool BWD, int LS_MAXC>
 __global__ void __launch_bounds__(LS_WARPS * 32)
 distortion_kernel(const float* __restrict__ s_vals, const float* __restrict__ weights, int B, int N,
                   float* __restrict__ per_ray, double* __restrict__ partials, const float* __restrict__ g_loss_ptr,
@@ -123,6 +125,7 @@ struct __align__(16) BoundsSmem {
 };
 
 // b[r,i] = sum_j w_j [t0_j <= R_i and t1_j >= L_i]  (closed intervals; distillation.py:25-29, App. B5)
+template <int LS_MAXC>
 __global__ void __launch_bounds__(LS_WARPS * 32)
 bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine, const float* __restrict__ t_coarse,
               int B, int N, float* __restrict__ b_out, double* __restrict__ total) {
@@ -204,16 +207,20 @@ bounds_kernel(const float* __restrict__ t_fine, const float* __restrict__ w_fine
 __global__ void __launch_bounds__(256)
 bounds_reduce_kernel(const float* __restrict__ b, int B, int N, int rows_per_block, double* __restrict__ total) {
   // blockDim = (128, 2): x over columns, y over row parity
-  __shared__ double sm[2][MIP360_MAX_SAMPLES];
-  const int n = threadIdx.x, y = threadIdx.y;
+  __shared__ double sm[2][128];
+  const int y = threadIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(B, r0 + rows_per_block);
-  double a = 0.0;
-  if (n < N)
-    for (int r = r0 + y; r < r1; r += 2) a += (double)b[(long long)r * N + n];
-  sm[y][n] = a;
-  __syncthreads();
-  if (y == 0 && n < N) atomicAdd(&total[n], sm[0][n] + sm[1][n]);
+  for (int n0 = 0; n0 < N; n0 += 128) {  // 128 columns at a time
+    const int n = n0 + threadIdx.x;
+    double a = 0.0;
+    if (n < N)
+      for (int r = r0 + y; r < r1; r += 2) a += (double)b[(long long)r * N + n];
+    sm[y][threadIdx.x] = a;
+    __syncthreads();
+    if (y == 0 && n < N) atomicAdd(&total[n], sm[0][threadIdx.x] + sm[1][threadIdx.x]);
+    __syncthreads();
+  }
 }
 
 // loss = sum relu(bnd - w)^2 / (w + 1e-6) / batch_div   (distillation.py:48-49)
@@ -458,7 +465,7 @@ int mip360_distortion_fwd(const float* s_vals, const float* weights, int B, int 
     if (rg && N == 32) distortion_rg_kernel<4, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
     else if (rg && N == 64) distortion_rg_kernel<8, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
     else if (rg && N == 128) distortion_rg_kernel<16, false><<<grid, RG_THREADS, 0, st>>>(s_vals, weights, B, per_ray, partials, nullptr, nullptr);
-    else distortion_kernel<false><<<grid, LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, per_ray, partials, nullptr, nullptr);
+    else LS_GENERIC(N, distortion_kernel<false,)<<<grid, LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, per_ray, partials, nullptr, nullptr);
     MIP_LAUNCH_CHECK();
   }
   reduce_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, 1.0, loss);
@@ -477,7 +484,7 @@ int mip360_distortion_bwd(const float* s_vals, const float* weights, int B, int 
     if (rg && N == 32) distortion_rg_kernel<4, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
     else if (rg && N == 64) distortion_rg_kernel<8, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
     else if (rg && N == 128) distortion_rg_kernel<16, true><<<rg_grid(B), RG_THREADS, 0, st>>>(s_vals, weights, B, nullptr, nullptr, g_loss_ptr, g_w);
-    else distortion_kernel<true><<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
+    else LS_GENERIC(N, distortion_kernel<true,)<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(s_vals, weights, B, N, nullptr, nullptr, g_loss_ptr, g_w);
   }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
@@ -502,7 +509,7 @@ int mip360_bounds(const float* t_fine, const float* w_fine, const float* t_coars
     if (rg && N == 32) bounds_rg_kernel<4><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
     else if (rg && N == 64) bounds_rg_kernel<8><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
     else if (rg && N == 128) bounds_rg_kernel<16><<<grid_rg, RG_THREADS, 0, st>>>(t_fine, w_fine, t_coarse, B, b_out, bound_total);
-    else bounds_kernel<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out, bound_total);
+    else LS_GENERIC(N, bounds_kernel<)<<<ray_grid(B, LS_WARPS), LS_WARPS * 32, 0, st>>>(t_fine, w_fine, t_coarse, B, N, b_out, bound_total);
   }
   MIP_LAUNCH_CHECK();
   return MIP360_OK;

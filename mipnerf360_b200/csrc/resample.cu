@@ -27,7 +27,10 @@ __device__ __forceinline__ void warp_blur(const float* wpad, float* wout, int N,
   }
 }
 
-// ray.py:15-27 on w[N] (shared memory) -> cdf[N+1]
+// ray.py:15-27 on w[N] (shared memory) -> cdf[N+1].  MAXC = intervals per lane (4: N <= 128, 16: N <= 512)
+constexpr int RS_MAXC_SMALL = 4, RS_MAXC_LARGE = (MIP360_MAX_SAMPLES + 31) / 32;
+#define RS_GENERIC(kernel, N) ((N) <= 32 * RS_MAXC_SMALL ? kernel<RS_MAXC_SMALL> : kernel<RS_MAXC_LARGE>)
+template <int MAXC>
 __device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int lane) {
   const int C = (N + 31) >> 5;  // contiguous chunk per lane
   const int j0 = lane * C;
@@ -43,9 +46,9 @@ __device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int 
   wsum = wsum + padding;
   // pdf and its inclusive scan
   float run = 0.f;
-  float pdf_loc[(MIP360_MAX_SAMPLES + 31) / 32];
+  float pdf_loc[MAXC];
 #pragma unroll
-  for (int c = 0; c < (MIP360_MAX_SAMPLES + 31) / 32; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     const int j = j0 + c;
     float p = 0.f;
     if (c < C && j < N) p = (w[j] + add) / wsum;
@@ -66,7 +69,7 @@ __device__ __forceinline__ void warp_cdf(const float* w, float* cdf, int N, int 
   pm = __shfl_up_sync(FULL_MASK, pm, 1);
   if (lane == 0) pm = 0.f;
 #pragma unroll
-  for (int c = 0; c < (MIP360_MAX_SAMPLES + 31) / 32; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     const int j = j0 + c;
     if (c < C && j < N - 1) cdf[j + 1] = fminf(1.f, fmaxf(off + pdf_loc[c], pm));
   }
@@ -117,6 +120,7 @@ __device__ __forceinline__ float invert_one(const float* cdf, const float* bins,
   return b0 + t * (b1 - b0);
 }
 
+template <int MAXC>
 __global__ void __launch_bounds__(RS_WARPS * 32)
 resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weights, const float* __restrict__ u_base,
                 const float* __restrict__ jitter, RngArgs rng, float jitter_scale, const float* __restrict__ directions,
@@ -144,7 +148,7 @@ resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weig
       for (int j = lane; j < N; j += 32) s.w[j] = s.wpad[j + 1];
     }
     __syncwarp();
-    warp_cdf(s.w, s.cdf, N, lane);
+    warp_cdf<MAXC>(s.w, s.cdf, N, lane);
     __syncwarp();
     for (int m = lane; m < K; m += 32) {
       float u = u_base[m];
@@ -189,6 +193,7 @@ blur_kernel(const float* __restrict__ weights, int B, int N, float padding, floa
   }
 }
 
+template <int MAXC>
 __global__ void __launch_bounds__(RS_WARPS * 32)
 cdf_kernel(const float* __restrict__ weights, int B, int N, float* __restrict__ cdf) {
   __shared__ ResampleSmem sm[RS_WARPS];
@@ -197,7 +202,7 @@ cdf_kernel(const float* __restrict__ weights, int B, int N, float* __restrict__ 
   for (int b = blockIdx.x * RS_WARPS + warp; b < B; b += gridDim.x * RS_WARPS) {
     for (int j = lane; j < N; j += 32) s.w[j] = weights[(long long)b * N + j];
     __syncwarp();
-    warp_cdf(s.w, s.cdf, N, lane);
+    warp_cdf<MAXC>(s.w, s.cdf, N, lane);
     __syncwarp();
     for (int k = lane; k <= N; k += 32) cdf[(long long)b * (N + 1) + k] = s.cdf[k];
     __syncwarp();
@@ -424,7 +429,7 @@ int mip360_resample_cdf(const float* weights, int B, int N, float* cdf, mip360_s
   MIP_REQUIRE(B <= 0 || (weights && cdf), "resample_cdf: null pointer");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "resample_cdf: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
-  cdf_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, cdf);
+  RS_GENERIC(cdf_kernel, N)<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(weights, B, N, cdf);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -470,7 +475,7 @@ int mip360_resample_sample(const float* t_vals, const float* weights, const floa
     resample_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale,
                                                              directions, norm_sq, B, resample_padding, blur, new_t);
   else
-    resample_kernel<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale,
+    RS_GENERIC(resample_kernel, N)<<<ray_grid(B, RS_WARPS), RS_WARPS * 32, 0, st>>>(t_vals, weights, u_base, jitter, rng, jitter_scale,
                                                                      directions, norm_sq, B, N, resample_padding, blur,
                                                                      new_t);
   MIP_LAUNCH_CHECK();

@@ -51,9 +51,7 @@ def _encode(rays, t_vals, viewdirs_encoding, contract_mode, batch_group=None, no
     group = the call is one ray shard of a data-parallel batch: the reference's batch-global contraction norm
     (App. A1) is summed over the group so that the sharded forward equals the unsharded one.  Only
     train.Trainer sets it; model(rays) / render_image never issue a collective."""
-    vd = _viewdir_features(viewdirs_encoding, rays.viewdirs)
-    if vd.shape[-1] != 16:
-        raise ValueError("the fused encoder packs 16 view-direction features (viewdir_min_deg=0, viewdir_max_deg=4)")
+    vd = _viewdir_features(viewdirs_encoding, rays.viewdirs)  # [B, 4 * (max_deg - min_deg)]
     # norm_sq: the batch's squared contraction norm, already accumulated by the kernel that produced t_vals
     if contract_mode == ops.CONTRACT_REFERENCE and batch_group is not None:
         if norm_sq is None:

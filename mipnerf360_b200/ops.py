@@ -55,6 +55,13 @@ def rng_advance(device):
     rng_epoch(device).add_(1)
 
 
+def manual_seed(seed):
+    """torch.manual_seed(seed) and a restart of the in-kernel generator's call counter (re-seeding torch with the SAME
+    value is not visible through torch.initial_seed(), so exact restarts go through this function)."""
+    torch.manual_seed(seed)
+    _Rng.torch_seed, _Rng.seed, _Rng.calls = torch.initial_seed(), _splitmix64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF), 0
+
+
 def rng_next(device):
     """(seed, stream id, epoch tensor) for the next randomized kernel call.  The key follows torch.manual_seed
     (torch.initial_seed()), every call gets its own stream id, so runs are reproducible per seed and call order."""
@@ -133,7 +140,8 @@ def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=N
         return dict(means=_empty((0, N, 3), dev) if want_means else None,
                     covs=_empty((0, N, 3, 3), dev) if want_covs else None,
                     enc=_empty((0, N, 42), dev) if want_enc else None,
-                    x=_empty((0, 64), dev, torch.bfloat16) if want_x else None, norm_sq=norm_sq)
+                    x=_empty((0, 64 if vdir_enc is None or vdir_enc.shape[-1] <= 22 else 128), dev, torch.bfloat16)
+                    if want_x else None, norm_sq=norm_sq)
     flags = int(bool(add_origins)) | (0 if stable else 2)
     if contract_mode == CONTRACT_REFERENCE and norm_sq is None:
         if stable:
@@ -147,11 +155,15 @@ def cast_ipe(t_vals, origins, directions, radii, vdir_enc=None, *, t0=None, t1=N
     means = _empty((B, N, 3), dev) if want_means else None
     covs = _empty((B, N, 3, 3), dev) if want_covs else None
     enc = _empty((B, N, 42), dev) if want_enc else None
-    x = _empty((B * N, 64), dev, torch.bfloat16) if want_x else None
     if want_x and vdir_enc is None:
         raise _lib.Mip360Error("cast_ipe: the bf16 MLP input needs vdir_enc")
-    call("mip360_cast_ipe", p0, p1, stride, ptr(origins), ptr(directions), ptr(vdir_enc), ptr(radii), ptr(norm_sq), B, N,
-         int(contract_mode), flags, ptr(means), ptr(covs), ptr(enc), ptr(x))
+    vd_dim = 0 if vdir_enc is None else int(vdir_enc.shape[-1])
+    x_cols = 64 if 42 + vd_dim <= 64 else 128  # bf16 row width = the first MLP layer's padded K
+    if want_x and (vd_dim % 4 or 42 + vd_dim > 128):
+        raise _lib.Mip360Error(f"cast_ipe: {vd_dim} view-direction features do not fit a 128-column MLP input row")
+    x = _empty((B * N, x_cols), dev, torch.bfloat16) if want_x else None
+    call("mip360_cast_ipe_x", p0, p1, stride, ptr(origins), ptr(directions), ptr(f32c(vdir_enc) if vdir_enc is not None else None),
+         vd_dim, ptr(radii), ptr(norm_sq), B, N, int(contract_mode), flags, ptr(means), ptr(covs), ptr(enc), ptr(x), x_cols)
     del keep
     out.update(means=means, covs=covs, enc=enc, x=x, norm_sq=norm_sq)
     return out

@@ -91,11 +91,13 @@ def render_frame(model, cam_to_world, height, width, focal, near, far, ndc=False
     rgb = torch.empty((m, 3), device=dev)
     d = torch.empty((m,), device=dev)
     a = torch.empty((m,), device=dev)
+    torch.cuda.nvtx.range_push("mip360/render_frame")
     with torch.no_grad():
         for i in range(0, m, chunks):
             c = min(chunks, m - i)
             chunk = ops.generate_rays(c2w, height, width, focal, near, far, ndc=ndc, ray_begin=lo + i, ray_count=c)
             rgb[i:i + c], d[i:i + c], a[i:i + c] = model(chunk)
+    torch.cuda.nvtx.range_pop()
     rgb8 = ops.to8b(rgb)  # the picture leaves the device (and crosses NVLink) as 3 B/pixel
     if world > 1:
         per = shard_bounds(n, 0, world, align=chunks)[1]

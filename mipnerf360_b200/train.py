@@ -29,6 +29,16 @@ from mipnerf360_b200.intern.loss import Loss_dist, Loss_nerf, mse_to_psnr
 from mipnerf360_b200.intern.ray import Rays
 
 
+@contextlib.contextmanager
+def _nvtx(name):
+    """NVTX range around a phase of the iteration (visible in Nsight Systems / ncu --nvtx; free without a profiler)."""
+    torch.cuda.nvtx.range_push("mip360/" + name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 def lr_at(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
     """intern/scheduler.py:13-23 evaluated at scheduler step `step` (host scalar math)."""
     if lr_delay_steps > 0:
@@ -293,30 +303,38 @@ class Trainer:
         """train.py:54-64: one proposal update.  Returns the loss (device scalar; data parallel: this shard's share of
         the global loss — the sum over ranks is the reference's value)."""
         m = self.model
-        with self._sharded_batch():
-            t_hat, w_hat = m.prop_net.forward(rays)
-            with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
-                _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
-        loss_prop = self._loss_prop(t, w, t_hat, w_hat)
-        self._zero_grad("prop")
-        loss_prop.backward()
-        self._optim("prop")
+        with _nvtx("prop_substep"):
+            with self._sharded_batch(), _nvtx("forward"):
+                t_hat, w_hat = m.prop_net.forward(rays)
+                with torch.no_grad():  # train.py:55-57: the nerf outputs are detached before use
+                    _, _, _, t, w, _ = m.nerf_net.forward(rays, t_hat, w_hat)
+            with _nvtx("loss_prop"):
+                loss_prop = self._loss_prop(t, w, t_hat, w_hat)
+            self._zero_grad("prop")
+            with _nvtx("backward"):
+                loss_prop.backward()
+            with _nvtx("allreduce+adamw"):
+                self._optim("prop")
         return loss_prop.detach()
 
     def nerf_substep(self, rays, pixels):
         """train.py:68-82: the NeRF update.  Returns (loss_all, psnr) (device scalars).  Data parallel: psnr and the
         photometric part of loss_all are those of the whole batch, the distortion part is the local shard's sum."""
         m = self.model
-        with self._sharded_batch():
-            with torch.no_grad():
-                t_hat, w_hat = m.prop_net.forward(rays)
-            rgb, _, _, t, w, s = m.nerf_net.forward(rays, t_hat, w_hat)
-        loss_nerf, psnr = self._loss_nerf(rgb, pixels)
-        loss_dist = Loss_dist(s, w)
-        loss_all = loss_nerf + self.dist_weight_decay * loss_dist
-        self._zero_grad("nerf")
-        loss_all.backward()
-        self._optim("nerf")
+        with _nvtx("nerf_substep"):
+            with self._sharded_batch(), _nvtx("forward"):
+                with torch.no_grad():
+                    t_hat, w_hat = m.prop_net.forward(rays)
+                rgb, _, _, t, w, s = m.nerf_net.forward(rays, t_hat, w_hat)
+            with _nvtx("losses"):
+                loss_nerf, psnr = self._loss_nerf(rgb, pixels)
+                loss_dist = Loss_dist(s, w)
+                loss_all = loss_nerf + self.dist_weight_decay * loss_dist
+            self._zero_grad("nerf")
+            with _nvtx("backward"):
+                loss_all.backward()
+            with _nvtx("allreduce+adamw"):
+                self._optim("nerf")
         return loss_all.detach(), psnr.detach()
 
     def _step_eager(self, rays, pixels):

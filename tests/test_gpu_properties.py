@@ -318,7 +318,7 @@ def test_empty_batches_and_size_limits(ops):
     assert float(ops.distortion_loss(e(0, N + 1), e(0, N))) == 0.0
     assert ops.bounds_per_ray(e(0, N + 1), e(0, N), e(0, N + 1)).shape == (0, N)
     assert ops.viewdir_enc(e(0, 3)).shape == (0, 16)
-    with pytest.raises(_lib.Mip360Error):  # more samples per ray than one warp holds
-        ops.resample(e(2, 131), e(2, 130), False, 0.01)
+    with pytest.raises(_lib.Mip360Error):  # more samples per ray than one warp holds (16 per lane: N <= 512)
+        ops.resample(e(2, 514), e(2, 513), False, 0.01)
     with pytest.raises(_lib.Mip360Error):
-        ops.composite(e(2, 200, 3), e(2, 200, 1), e(2, 201), e(2, 3), False)
+        ops.composite(e(2, 600, 3), e(2, 600, 1), e(2, 601), e(2, 3), False)

@@ -473,7 +473,8 @@ def test_in_kernel_random_draws_match_the_restated_generator(ops, B, N):
     ref_n = O.frustum_norm_sq(t_ref, d)
     assert abs(float(nsq) - ref_n) <= 1e-6 * ref_n
     pre = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, d.to(dev), B, N)
-    assert abs(float(nsq) - float(pre)) <= 1e-12 * float(pre)         # same per-sample arithmetic as the pre-pass
+    # the pre-pass kernels: same per-sample fp32 arithmetic for N in {32,64,128}; the generic one squares in fp64
+    assert abs(float(nsq) - float(pre)) <= (1e-12 if N in (32, 64, 128) else 1e-8) * float(pre)
     # resampling: jitter = u01 * (1/M - eps), the way torch's uniform_(0, 1/M - eps) scales its draw
     w = torch.rand(B, N, generator=g) ** 2 * 0.2
     jit = torch.from_numpy(philox.uniform(seed, stream_id + 1, 5, (B, N + 1))) * torch.tensor(ops.jitter_scale(N + 1))
@@ -482,17 +483,22 @@ def test_in_kernel_random_draws_match_the_restated_generator(ops, B, N):
     same = ops.resample(t, w.to(dev), True, 0.01, jitter=jit.to(dev))
     assert torch.equal(new_t, same)                                     # in-kernel draw == the same numbers handed in
     ref_t = O.resample_t_vals(t_ref, w, True, 0.01, jitter=jit)
-    close(new_t, ref_t, rtol=1e-5, atol=1e-6)
+    # the kernel's own CDF differs from torch's cumsum by rounding, and the inverse CDF amplifies that by
+    # (bin width / CDF step): far bins of a near = 0.1, far = 10 ray are ~5 wide.  Given the SAME CDF the samples are
+    # bit-exact (test_resample_vs_oracle, two-stage API).
+    close(new_t, ref_t, rtol=1e-4, atol=2e-5)
     pre2 = ops.frustum_norm_sq(new_t.data_ptr(), new_t.data_ptr() + 4, N + 1, d.to(dev), B, N)
-    assert abs(float(nsq2) - float(pre2)) <= 1e-12 * float(pre2)
+    assert abs(float(nsq2) - float(pre2)) <= (1e-12 if N in (32, 64, 128) else 1e-8) * float(pre2)
     # another replay epoch / call site gives other numbers; the default path follows torch.manual_seed
     epoch2 = torch.tensor([6], dtype=torch.int64, device=dev)
     assert not torch.equal(t, ops.level0_t_vals(near.to(dev), far.to(dev), N, True, rng=(seed, stream_id, epoch2)))
-    torch.manual_seed(99)
+    ops.manual_seed(99)
     a1, a2 = ops.level0_t_vals(near.to(dev), far.to(dev), N, True), ops.level0_t_vals(near.to(dev), far.to(dev), N, True)
-    torch.manual_seed(99)
+    ops.manual_seed(99)
     b1 = ops.level0_t_vals(near.to(dev), far.to(dev), N, True)
-    assert torch.equal(a1, b1) and not torch.equal(a1, a2)
+    torch.manual_seed(100)   # a new torch seed re-keys the generator as well
+    c1 = ops.level0_t_vals(near.to(dev), far.to(dev), N, True)
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2) and not torch.equal(a1, c1)
     assert (a1[:, 1:] >= a1[:, :-1]).all()
 
 
@@ -523,3 +529,118 @@ def test_fused_composite_t_to_s_and_bound_totals(ops, B, N):
     torch.testing.assert_close(tot, two_pass, rtol=1e-12, atol=1e-15)
     ref = O.bounds_per_ray(t.cpu().double(), w.cpu().double(), tc.cpu().double()).sum(0)
     torch.testing.assert_close(tot.cpu(), ref, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# more than 128 samples per ray (the reference has no limit; here one warp holds up to 512)
+# ---------------------------------------------------------------------------------------------------
+def test_more_than_128_samples_vs_literal_reference(golden2, ops):
+    c = golden2.case("n150_sample", DEV)
+    rays = rays_from(c, DEV)
+    N = int(c["N"])
+    t = ops.level0_t_vals(rays.near, rays.far, N, True, t_rand=c["t_rand"])
+    close(t, c["t_vals"], atol=0)
+    out = ops.cast_ipe(t, rays.origins, rays.directions, rays.radii, want_means=True, want_covs=True)
+    close(out["means"], c["means"])
+    cov_close(out["covs"], c["covs"], 2e-5)
+    c = golden2.case("n150_pdf", DEV)
+    M = int(c["M"])
+    cdf = ops.resample_cdf(c["weights"])
+    close(cdf, O.pdf_to_cdf(c["weights"].cpu()), atol=1e-6)
+    u = O.pdf_uniforms(c["bins"].shape[0], M, True, jitter=c["jitter"].cpu()).contiguous()
+    ref_s, ref_i = O.invert_cdf(c["bins"].cpu(), O.pdf_to_cdf(c["weights"].cpu()), u)
+    s, idx = ops.resample_invert(c["bins"], O.pdf_to_cdf(c["weights"].cpu()).to(DEV), u.to(DEV), return_idx=True)
+    assert torch.equal(idx.cpu().long(), ref_i) and torch.equal(s.cpu(), ref_s)   # bit-exact given the same CDF and u
+    assert torch.equal(ref_s, c["samples"].cpu())
+    fused = ops.resample(c["bins"], c["weights"], True, 0.0, jitter=c["jitter"], blur=False)
+    close(fused, c["samples"], rtol=1e-4, atol=2e-5)
+    c = golden2.case("n150_resample", DEV)
+    rays = rays_from(c, DEV)
+    new_t = ops.resample(c["t_in"], c["weights"], True, 0.01, jitter=c["jitter"])
+    close(new_t, c["t_vals"], rtol=1e-4, atol=2e-5)
+    c = golden2.case("n150_render", DEV)
+    comp, dist, acc, w = ops.composite(c["rgb"], c["density"], c["t_vals"], c["dirs"], True)
+    for a, b in ((comp, "comp_rgb"), (dist, "distance"), (acc, "acc"), (w, "weights")):
+        close(a, c[b], rtol=1e-5, atol=1e-6, msg=b)
+    wo = ops.density_to_weight(c["t_vals"], c["density"], c["dirs"])
+    close(wo, c["weights"], rtol=1e-5, atol=1e-6)
+    c = golden2.case("n150_interlevel", DEV)
+    from mipnerf360_b200.intern.distillation import bounds
+    from mipnerf360_b200.intern.loss import Loss_dist, Loss_prop
+    close(bounds(c["t_fine"], c["w_fine"], c["t_coarse"]), c["bounds"], rtol=1e-5, atol=1e-7)
+    close(Loss_prop(c["t_fine"], c["w_fine"], c["t_coarse"], c["w_coarse"]), c["Loss_prop"], rtol=1e-5)
+    c = golden2.case("n150_distortion", DEV)
+    close(Loss_dist(c["s_vals"], c["weights"]), c["loss"], rtol=2e-5)
+    # gradients at N = 150 and the largest supported N against fp64 autograd through the oracle
+    for B, N in ((6, 150), (3, 512)):
+        g = torch.Generator().manual_seed(N)
+        t = (torch.rand(B, N + 1, generator=g) * 0.1).cumsum(-1) + 0.2
+        rgb, dens, dirs = torch.rand(B, N, 3, generator=g), torch.rand(B, N, 1, generator=g) * 2, torch.randn(B, 3, generator=g)
+        gc, gw = torch.randn(B, 3, generator=g), torch.randn(B, N, generator=g)
+        dens_r = dens.double().requires_grad_(True)
+        comp_r, _, _, w_r = O.volumetric_rendering(rgb.double(), dens_r, t.double(), dirs.double(), False)
+        s_r = t.double() / t.double()[:, -1:]
+        ld_r = O.loss_dist(s_r, w_r)
+        ((comp_r * gc.double()).sum() + (w_r * gw.double()).sum() + ld_r).backward()
+        dens_d = dens.to(DEV).requires_grad_(True)
+        comp_d, _, _, w_d = ops.composite(rgb.to(DEV), dens_d, t.to(DEV), dirs.to(DEV), False)
+        ld_d = ops.distortion_loss((t / t[:, -1:]).to(DEV), w_d)
+        ((comp_d * gc.to(DEV)).sum() + (w_d * gw.to(DEV)).sum() + ld_d).backward()
+        close(ld_d, ld_r.float(), rtol=2e-5)
+        scale = float(dens_r.grad.abs().max())
+        close(dens_d.grad, dens_r.grad.float(), rtol=2e-4, atol=2e-5 * scale, msg=f"N={N}")
+    # a whole model with 150 samples per ray runs and trains
+    from mipnerf360_b200.model import mipNeRF360
+    m = mipNeRF360(randomized=True, num_samples=150, hidden_proposal=64, hidden_nerf=128, device=torch.device(DEV))
+    g = torch.Generator().manual_seed(1)
+    o, d = torch.randn(16, 3, generator=g), torch.randn(16, 3, generator=g)
+    rays = O.Rays(*[x.to(DEV) for x in (o, d, d / d.norm(dim=-1, keepdim=True), torch.full((16, 1), 1e-3),
+                                        torch.full((16, 1), 0.1), torch.full((16, 1), 10.0))])
+    rgb, dist, acc = m(rays)
+    rgb.sum().backward()
+    assert rgb.shape == (16, 3) and torch.isfinite(rgb).all() and m.nerf_net.model[0].weight.grad is not None
+
+
+def test_other_viewdir_degrees_vs_literal_reference_and_oracle(golden2, ops):
+    """viewdir_min_deg / viewdir_max_deg other than (0, 4): 8 features (input width 50, 64-column rows) against the
+    literal reference, 24 features (input width 66 -> 128-column rows, first layer K padded to 128) against the oracle."""
+    c = golden2.case("model_vd13", DEV)
+    sd = golden2.case("model_vd13_sd")
+    m = model_from_sd(sd, int(c["N"]), int(c["HP"]), int(c["HN"]), viewdir_min_deg=1, viewdir_max_deg=3)
+    assert m.prop_net.model[0].weight.shape[1] == 50
+    rgb, dist, acc = m(rays_from(c, DEV))
+    close(rgb, c["fwd_rgb"], rtol=2e-2, atol=5e-3, msg="rgb")
+    close(acc, c["fwd_acc"], rtol=2e-2, atol=5e-3, msg="acc")
+    close(dist, c["fwd_dist"], rtol=2e-2, atol=2e-2, msg="dist")
+    # the encoder rows themselves, both widths, against the exact fp32 encodings
+    g = torch.Generator().manual_seed(8)
+    B, N = 40, 16
+    o, d = torch.randn(B, 3, generator=g), torch.randn(B, 3, generator=g)
+    rays = O.Rays(o, d, d / d.norm(dim=-1, keepdim=True), torch.full((B, 1), 1e-3), torch.full((B, 1), 0.1), torch.full((B, 1), 10.0))
+    rays_d = O.Rays(*[x.to(DEV) for x in rays])
+    t = ops.level0_t_vals(rays_d.near, rays_d.far, N, False)
+    for lo, hi in ((1, 3), (0, 5), (0, 6), (2, 9)):
+        vd = ops.viewdir_enc(rays_d.viewdirs, lo, hi)
+        out = ops.cast_ipe(t, rays_d.origins, rays_d.directions, rays_d.radii, vd, want_x=True, want_enc=True)
+        width = 64 if 42 + 4 * (hi - lo) <= 64 else 128
+        x = out["x"].float().view(B, N, width)
+        assert float((x[..., :42] - out["enc"]).abs().max()) <= 2 ** -8 + 1e-3
+        close(x[..., 42:42 + 4 * (hi - lo)], vd[:, None, :].expand(-1, N, -1), rtol=0, atol=2 ** -8)
+        assert float(x[..., 42 + 4 * (hi - lo):].abs().max()) == 0.0
+    # a whole model with 24 view-direction features against the fp32 oracle, forward and backward
+    from mipnerf360_b200.model import mipNeRF360
+    torch.manual_seed(2)
+    m = mipNeRF360(randomized=False, num_samples=N, hidden_proposal=64, hidden_nerf=128, viewdir_min_deg=0, viewdir_max_deg=6,
+                   device=torch.device(DEV))
+    assert m.nerf_net.model[0].weight.shape[1] == 66
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    rgb, dist, acc = m(rays_d)
+    ref = O.model_forward(sd, rays, N, False, viewdir_deg=(0, 6))
+    close(rgb, ref[0], rtol=2e-2, atol=5e-3, msg="rgb wide")
+    close(acc, ref[2], rtol=2e-2, atol=5e-3, msg="acc wide")
+    rgb.sum().backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.model_forward(params, rays, N, False, viewdir_deg=(0, 6))[0].sum().backward()
+    gk = "nerf_net.model.0.weight"
+    gd = dict(m.named_parameters())[gk].grad.cpu()
+    assert float((gd - params[gk].grad).norm() / params[gk].grad.norm()) < 5e-2
