@@ -80,9 +80,12 @@ def cpu_iteration(O, params, opt, rays, pixels, N):
     return float(la.detach())
 
 
-def run_cpu(sample_rays, steps, warmup):
-    """The reference's algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample of the workload."""
+def run_cpu(sample_rays, steps, warmup, literal=False):
+    """The reference's algorithm (oracle port, fp32 torch CPU, all host threads) on a bounded sample of the workload.
+    literal=True keeps the reference's per-sample autograd-Jacobian loop (parameterization.py:77-79) instead of its closed
+    form: the algorithm exactly as the reference executes it, ~0.17 ms per sample and level."""
     from oracle import mip360_oracle as O
+    O.LITERAL_CONTRACT = bool(literal)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = O.init_state_dict(seed=0)
@@ -95,6 +98,7 @@ def run_cpu(sample_rays, steps, warmup):
     for _ in range(steps):
         cpu_iteration(O, params, opt, rays, pixels, N_SAMPLES)
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    O.LITERAL_CONTRACT = False
     return dict(value=sample_rays / dt, ms_per_step=dt * 1e3, cores=cores, threads=torch.get_num_threads())
 
 
@@ -157,22 +161,27 @@ class ClockSampler:
 # per-kernel accounting (algorithmic work per launch, SURVEY §8d / BASELINE.md §4)
 # -------------------------------------------------------------------------------------------------
 def kernel_work(name, a):
-    """(kind, units) for a profiled call: kind 'tensor' -> FLOP, 'hbm' -> bytes.  `a` = the int arguments."""
+    """(kind, units) for a profiled call: kind 'tensor' -> FLOP, 'hbm' -> bytes.  `a` = the int arguments of the C call."""
     if name == "mip360_linear_fwd":       # M, N, K, act, n_valid
         return "tensor", 2.0 * a[0] * a[1] * a[2]
+    if name == "mip360_linear_fwd_head":  # M, N, K, act : trunk layer + the 4 head columns in its epilogue
+        return "tensor", 2.0 * a[0] * a[1] * a[2] + 2.0 * a[0] * a[1] * 4
     if name == "mip360_linear_dgrad":     # M, N, K, act
         return "tensor", 2.0 * a[0] * a[1] * a[2]
     if name == "mip360_linear_wgrad":     # M, N, K
         return "tensor", 2.0 * a[0] * a[1] * a[2]
-    if name == "mip360_cast_ipe":         # t_stride, B, N, mode, add_origins : bf16 [N,64] output variant
-        B, N = a[1], a[2]
-        return "hbm", B * (48.0 + 4 * (N + 1) + 128 * N)
-    if name == "mip360_resample":         # B, N, blur
+    if name == "mip360_cast_ipe_x":       # t_stride, vd_dim, B, N, mode, flags, x_cols : bf16 [N, x_cols] output variant
+        B, N, cols = a[2], a[3], a[6]
+        return "hbm", B * (48.0 + 4 * (N + 1) + 2 * cols * N)
+    if name == "mip360_level0_sample":    # use_rng, seed, stream, B, N : writes the knots (reads 8 B/ray)
+        B, N = a[-2], a[-1]
+        return "hbm", B * (4.0 * (N + 1) + 8 + 12)
+    if name == "mip360_resample_sample":  # use_rng, seed, stream, B, N, blur : bins + weights in, knots out
+        B, N = a[-3], a[-2]
+        return "hbm", B * (4.0 * (3 * N + 2) + 12)
+    if name == "mip360_composite_fwd_s":  # B, N, head_mode, white : + s_vals and t_shift rows
         B, N = a[0], a[1]
-        return "hbm", B * (4.0 * (3 * N + 2) + 4 * (N + 1))
-    if name == "mip360_composite_fwd":    # B, N, head_mode, white
-        B, N = a[0], a[1]
-        return "hbm", B * (16.0 * N + 4 * (N + 1) + 12 + 20 + 4 * N)
+        return "hbm", B * (16.0 * N + 4 * (N + 1) + 12 + 20 + 4 * N + 8 * (N + 1) + 8)
     if name == "mip360_composite_bwd":
         B, N = a[0], a[1]
         return "hbm", B * (16.0 * N + 4 * (N + 1) + 12 + 16 + 4 * N + 16 * N)
@@ -183,8 +192,12 @@ def kernel_work(name, a):
         return "hbm", a[0] * (4.0 * (2 * a[1] + 1) + 4)
     if name == "mip360_distortion_bwd":
         return "hbm", a[0] * (4.0 * (2 * a[1] + 1) + 4 * a[1])
-    if name == "mip360_bounds_per_ray":
-        return "hbm", a[0] * (4.0 * (3 * a[1] + 2) + 4 * a[1])
+    if name == "mip360_bounds":           # B, N : two knot rows + fine weights in, N totals out
+        return "hbm", a[0] * (4.0 * (3 * a[1] + 2))
+    if name in ("mip360_interlevel_fwd", "mip360_interlevel_bwd"):
+        return "hbm", a[0] * a[1] * (8.0 if name.endswith("bwd") else 4.0)
+    if name == "mip360_adamw_pack":       # entries, tiles, ... : p, g, m, v read, p, m, v, g written, bf16 W and W^T written
+        return "hbm", a[1] * 1024 * (16.0 + 16 + 4)
     return "hbm", 0.0
 
 
@@ -481,6 +494,12 @@ def main():
             out["cpu_baseline"] = {"value": r["value"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
                                    "sample": f"{args.cpu_sample_rays} rays of the same iteration, 2 timed steps, "
                                              f"oracle port of the reference (fp32 torch CPU, {r['threads']} threads)"}
+            # the algorithm exactly as the reference executes it (per-sample autograd Jacobians): one step
+            # of 16 rays = 6 levels x 1024 jacobian() calls, extrapolated linearly (the loop is O(rays x samples))
+            lit = run_cpu(16, 1, 0, literal=True)
+            out["cpu_baseline"]["literal_jacobian_loop"] = {
+                "value": lit["value"], "unit": "rays/s", "sample": "16 rays, 1 step, per-sample jacobian() loop kept",
+                "note": "what /root/reference does on this host; its own GPU path is launch-bound the same way (SURVEY A13)"}
         print(json.dumps(out), flush=True)
     if world > 1:
         # captured graphs hold NCCL work: drop them and drain the device before the communicator goes away, and do not

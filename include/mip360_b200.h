@@ -156,6 +156,9 @@ int mip360_resample_sample(const float* t_vals, const float* weights, const floa
  *   head_mode 0: rgb [B,N,3] and density [B,N] are final values (volumetric_rendering as is).
  *   head_mode 1: raw [B,N,4] = (sigmoid density head, sigmoid colour head) straight from the MLP;
  *     density = softplus(raw0 + density_bias), rgb = raw123*(1+2*rgb_padding) - rgb_padding.
+ *   head_mode 2: raw [B,N,4] = the heads' pre-activation sums without bias (mip360_mlp_fwd_fused_head); the bias
+ *     head_bias[4] (device) and the Sigmoid of model.py:150-158 are applied here, then as head_mode 1.  Backward:
+ *     g_raw = dL/d(pre-activation), the Sigmoid derivative included.
  *   weights-only variant (density_to_weight): density_mode 0 = density given, 1 = raw logits,
  *     density = softplus(raw + density_bias) (model.py:92).
  *   Backward: g_rgb [B,3], g_acc [B], g_dist [B], g_w [B,N] (any may be NULL) -> gradient w.r.t. rgb/density
@@ -172,15 +175,17 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          float* comp_rgb, float* distance, float* acc, float* weights, mip360_stream_t stream);
 /* mip360_composite_fwd plus model.py:196 in the same pass: s_vals [B,N+1] = t_to_s(t_vals, near, far) and (optional)
- * t_shift = t_vals + 1e-6 exactly as mip360_t_to_s produces them (near, far [B]). */
+ * t_shift = t_vals + 1e-6 exactly as mip360_t_to_s produces them (near, far [B]); head_bias [4] for head_mode 2. */
 int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                            int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                            float* comp_rgb, float* distance, float* acc, float* weights, const float* near,
-                           const float* far, float* s_vals, float* t_shift, mip360_stream_t stream);
+                           const float* far, float* s_vals, float* t_shift, const float* head_bias,
+                           mip360_stream_t stream);
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs,
                          int B, int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_dist, const float* g_w,
-                         float* g_rgb_in, float* g_density, float* g_raw, mip360_stream_t stream);
+                         float* g_rgb_in, float* g_density, float* g_raw, const float* head_bias,
+                         mip360_stream_t stream);
 int mip360_density_to_weight_fwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
                                  int density_mode, float density_bias, float* weights, mip360_stream_t stream);
 int mip360_density_to_weight_bwd(const float* density, const float* t_vals, const float* dirs, int B, int N,
@@ -244,6 +249,13 @@ int mip360_interlevel_bwd(const float* w_hat, const float* b_per_ray, const doub
  * ------------------------------------------------------------------------------------------ */
 int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
                       uint16_t* out_bf16, float* out_f32, int n_valid, mip360_stream_t stream);
+/* The last trunk layer with the (<= 4 wide) head folded into its epilogue (model.py:147-158,180-181): Y as above
+ * (out_bf16 may be NULL: inference does not need the trunk output) and head_out[M,4] += act(...) * head_w4 with head_w4
+ * fp32 [N,4] (column-interleaved head weights).  head_out is ACCUMULATED into (the column tiles of a row arrive from
+ * different CTAs): zero it first; bias and head activation are applied by the consumer (mip360_composite_fwd_s,
+ * head_mode 2). */
+int mip360_linear_fwd_head(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
+                           uint16_t* out_bf16, const float* head_w4, float* head_out, mip360_stream_t stream);
 int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,
                         uint16_t* dX, mip360_stream_t stream);
 int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int K, float* dW, float* db,
@@ -266,6 +278,11 @@ typedef struct mip360_layer {
  *   for the head, all ACCUMULATED into (split-K atomics).  dz_head [M,64], dz0, dz1 [M, max n_pad]: bf16 scratch. */
 int mip360_mlp_fwd(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const mip360_layer* head,
                    int n_valid, uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream);
+/* mip360_mlp_fwd with the head folded into the last trunk layer (mip360_linear_fwd_head): head_w4 fp32 [k_pad, 4].
+ * `out` [M,4] receives the head's PRE-activation sums WITHOUT bias (zeroed inside).  With n_act_bufs == 2 the last trunk
+ * activation is not written at all. */
+int mip360_mlp_fwd_fused_head(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const float* head_w4,
+                              uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream);
 int mip360_mlp_bwd(const float* g_out, const float* out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
                    const mip360_layer* head, int n_valid, uint16_t* const* acts, float* const* dW, float* const* db,
                    uint16_t* dz_head, uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream);
@@ -352,6 +369,8 @@ typedef struct mip360_pack_entry {
   uint16_t* Wb;
   uint16_t* Wt;
   float* bias;
+  float* w4;             /* NULL, or fp32 [k_pad, 4]: rows 0..3 of the padded matrix (bf16-rounded), column-interleaved —
+                            the head weights as mip360_linear_fwd_head reads them */
 } mip360_pack_entry;
 int mip360_adamw_pack(const mip360_pack_entry* entries, int n_entries, int total_tiles, float* p, float* g, float* m,
                       float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,

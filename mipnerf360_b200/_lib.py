@@ -44,8 +44,8 @@ SIGNATURES = {
     "mip360_resample_sample": [P, P, P, P, c_int, ctypes.c_ulonglong, ctypes.c_uint, P, c_float, P, P, c_int, c_int, c_float,
                                c_int, P, P],
     "mip360_composite_fwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P],
-    "mip360_composite_fwd_s": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P, P],
-    "mip360_composite_bwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P],
+    "mip360_composite_fwd_s": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P, P, P],
+    "mip360_composite_bwd": [P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P, P],
     "mip360_density_to_weight_fwd": [P, P, P, c_int, c_int, c_int, c_float, P, P],
     "mip360_density_to_weight_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_head_grad_pack": [P, P, c_longlong, c_int, c_int, P, P],
@@ -60,10 +60,12 @@ SIGNATURES = {
     "mip360_interlevel_fwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_interlevel_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_linear_fwd": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, P],
+    "mip360_linear_fwd_head": [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "mip360_linear_dgrad": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "mip360_linear_wgrad": [P, P, c_int, c_int, c_int, P, P, P],
     "mip360_cast_weight": [P, c_int, c_int, c_int, c_int, P, P, P],
     "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
+    "mip360_mlp_fwd_fused_head": [P, c_int, P, c_int, P, P, c_int, P, P],
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
     "mip360_generate_rays_range": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_longlong,
@@ -94,7 +96,8 @@ class Layer(ctypes.Structure):
 class PackEntry(ctypes.Structure):
     """struct mip360_pack_entry of include/mip360_b200.h."""
     _fields_ = [("w_src", c_void_p * 2), ("b_src", c_void_p * 2), ("rows", c_int * 2), ("K", c_int), ("n_pad", c_int),
-                ("k_pad", c_int), ("tile_begin", c_int), ("Wb", c_void_p), ("Wt", c_void_p), ("bias", c_void_p)]
+                ("k_pad", c_int), ("tile_begin", c_int), ("Wb", c_void_p), ("Wt", c_void_p), ("bias", c_void_p),
+                ("w4", c_void_p)]
 
 
 _lib = None

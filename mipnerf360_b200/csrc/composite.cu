@@ -51,17 +51,31 @@ __device__ __forceinline__ void ray_weights(const CompositeSmem& s, int N, int C
   }
 }
 
+// head_mode 2: raw holds the heads' pre-activation sums without bias -> Sigmoid(raw + bias) (model.py:150-158)
+__device__ __forceinline__ float4 head_sigmoid(float4 v, const float* __restrict__ head_bias) {
+  return make_float4(sigmoid_f(v.x + __ldg(head_bias)), sigmoid_f(v.y + __ldg(head_bias + 1)),
+                     sigmoid_f(v.z + __ldg(head_bias + 2)), sigmoid_f(v.w + __ldg(head_bias + 3)));
+}
+// ... and its derivative y (1 - y) folded into the gradient of the four head outputs; y0 is kept, the colours are
+// recovered from the padded values c = y * scale - pad
+__device__ __forceinline__ float4 head_sigmoid_bwd(float4 g, float y0, float c1, float c2, float c3, float scale, float pad) {
+  const float y1 = (c1 + pad) / scale, y2 = (c2 + pad) / scale, y3 = (c3 + pad) / scale;
+  return make_float4(g.x * (y0 * (1.f - y0)), g.y * (y1 * (1.f - y1)), g.z * (y2 * (1.f - y2)), g.w * (y3 * (1.f - y3)));
+}
+
 // stage one ray.  mode_full: rgb too.  head_mode 1: raw [N,4] post-sigmoid head outputs.
 __device__ __forceinline__ void stage_ray(CompositeSmem& s, const float* rgb_or_raw, const float* density,
                                           const float* t_vals, long long b, int N, int head_mode, bool with_rgb,
-                                          int density_mode, float density_bias, float rgb_padding, int lane) {
+                                          int density_mode, float density_bias, float rgb_padding, int lane,
+                                          const float* head_bias) {
   const float* trow = t_vals + b * (N + 1);
   for (int k = lane; k <= N; k += 32) s.t[k] = trow[k];
-  if (head_mode == 1) {
+  if (head_mode >= 1) {
     const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + b * N;
     const float scale = 1.f + 2.f * rgb_padding;
     for (int j = lane; j < N; j += 32) {
-      const float4 v = raw4[j];
+      float4 v = raw4[j];
+      if (head_mode == 2) v = head_sigmoid(v, head_bias);
       s.aux[j] = v.x;
       s.sigma[j] = softplus_f(v.x + density_bias);
       s.rgb[j * 3 + 0] = v.y * scale - rgb_padding;
@@ -99,14 +113,14 @@ composite_fwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                      float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
                      float* __restrict__ weights, const float* __restrict__ near, const float* __restrict__ far,
-                     float* __restrict__ s_vals, float* __restrict__ t_shift) {
+                     float* __restrict__ s_vals, float* __restrict__ t_shift, const float* __restrict__ head_bias) {
   __shared__ CompositeSmem sm[CP_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CompositeSmem& s = sm[warp];
   const int C = (N + 31) >> 5, j0 = lane * C;
   for (int b = blockIdx.x * CP_WARPS + warp; b < B; b += gridDim.x * CP_WARPS) {
     stage_ray(s, rgb_or_raw, density, t_vals, b, N, head_mode, !weights_only, density_mode, density_bias, rgb_padding,
-              lane);
+              lane, head_bias);
     const float dx = dirs[b * 3], dy = dirs[b * 3 + 1], dz = dirs[b * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     __syncwarp();
@@ -165,7 +179,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
                      int weights_only, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_dist,
                      const float* __restrict__ g_w, float* __restrict__ g_rgb_in, float* __restrict__ g_density,
-                     float* __restrict__ g_raw) {
+                     float* __restrict__ g_raw, const float* __restrict__ head_bias) {
   __shared__ CompositeSmem sm[CP_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CompositeSmem& s = sm[warp];
@@ -173,7 +187,7 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
   const float cscale = 1.f + 2.f * rgb_padding;
   for (int b = blockIdx.x * CP_WARPS + warp; b < B; b += gridDim.x * CP_WARPS) {
     stage_ray(s, rgb_or_raw, density, t_vals, b, N, head_mode, !weights_only, density_mode, density_bias, rgb_padding,
-              lane);
+              lane, head_bias);
     if (g_w) {
       for (int j = lane; j < N; j += 32) s.gw[j] = g_w[(long long)b * N + j];
     }
@@ -227,12 +241,15 @@ composite_bwd_kernel(const float* __restrict__ rgb_or_raw, const float* __restri
         const float g_dd = G[c] * r.T[c] * expf(-r.dd[c]) - (off + excl_rev[c]);
         const float g_sigma = g_dd * r.delta[c];
         const long long e = (long long)b * N + j;
-        if (head_mode == 1) {
+        if (head_mode >= 1) {
           const float y0 = s.aux[j];
           // sigma = softplus(y0 + bias): d/dy0 = sigmoid(y0 + bias); colour = y*(1+2p) - p
           const float g_y0 = g_sigma * sigmoid_f(y0 + density_bias);
           const float g_y1 = r.w[c] * gr * cscale, g_y2 = r.w[c] * gg * cscale, g_y3 = r.w[c] * gb * cscale;
-          if (g_raw) reinterpret_cast<float4*>(g_raw)[e] = make_float4(g_y0, g_y1, g_y2, g_y3);
+          float4 gy = make_float4(g_y0, g_y1, g_y2, g_y3);
+          if (head_mode == 2)
+            gy = head_sigmoid_bwd(gy, y0, s.rgb[j * 3], s.rgb[j * 3 + 1], s.rgb[j * 3 + 2], cscale, rgb_padding);
+          if (g_raw) reinterpret_cast<float4*>(g_raw)[e] = gy;
         } else {
           if (density_mode == 1) {
             const float g_z = g_sigma * sigmoid_f(s.aux[j] + density_bias);
@@ -268,18 +285,22 @@ template <int E>
 __device__ __forceinline__ void rg_fetch(RgRay<E>& r, const float* __restrict__ rgb_or_raw,
                                          const float* __restrict__ density, const float* __restrict__ t_vals,
                                          const float* __restrict__ dirs, long long ray, int N, int gl, int head_mode,
-                                         bool want_rgb, float rgb_padding) {
+                                         bool want_rgb, float rgb_padding, const float* __restrict__ head_bias) {
   const int j0 = gl * E;
   rg_load_knots<E>(t_vals + ray * (N + 1), j0, r.t);
 #pragma unroll
   for (int i = 0; i < 3; ++i) r.d[i] = __ldg(dirs + ray * 3 + i);
-  if (head_mode == 1) {
+  if (head_mode >= 1) {
     // one 16-byte load per sample: density logit and colour together (whole sectors, a single pass over the rows)
     const float4* raw4 = reinterpret_cast<const float4*>(rgb_or_raw) + ray * N + j0;
     const float scale = 1.f + 2.f * rgb_padding;
     float4 v[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) v[i] = __ldg(raw4 + i);
+    if (head_mode == 2) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) v[i] = head_sigmoid(v[i], head_bias);
+    }
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       r.aux[i] = v[i].x;
@@ -307,7 +328,7 @@ template <int E>
 __device__ __forceinline__ void rg_weights(RgRay<E>& r, int gl, int head_mode, int density_mode, float density_bias) {
 #pragma unroll
   for (int i = 0; i < E; ++i)
-    r.sigma[i] = (head_mode == 1 || density_mode == 1) ? softplus_f(r.aux[i] + density_bias) : r.aux[i];
+    r.sigma[i] = (head_mode >= 1 || density_mode == 1) ? softplus_f(r.aux[i] + density_bias) : r.aux[i];
   const float dnorm = sqrtf(r.d[0] * r.d[0] + r.d[1] * r.d[1] + r.d[2] * r.d[2]);
   float run = 0.f, excl[E];
 #pragma unroll
@@ -333,7 +354,7 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
                         int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                         float* __restrict__ comp_rgb, float* __restrict__ distance, float* __restrict__ acc_out,
                         float* __restrict__ weights, const float* __restrict__ near, const float* __restrict__ far,
-                        float* __restrict__ s_vals, float* __restrict__ t_shift) {
+                        float* __restrict__ s_vals, float* __restrict__ t_shift, const float* __restrict__ head_bias) {
   constexpr int N = E * RG_LANES;
   constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
@@ -342,7 +363,7 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
-    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
+    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding, head_bias);
     float nr = 0.f, fr = 0.f;
     if (!WO && s_vals) { nr = __ldg(near + ray); fr = __ldg(far + ray); }
     rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
@@ -395,7 +416,7 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
                         int /*weights_only*/, int density_mode, float density_bias, float rgb_padding, int white_bkgd,
                         const float* __restrict__ g_rgb, const float* __restrict__ g_acc, const float* __restrict__ g_dist,
                         const float* __restrict__ g_w, float* __restrict__ g_rgb_in, float* __restrict__ g_density,
-                        float* __restrict__ g_raw) {
+                        float* __restrict__ g_raw, const float* __restrict__ head_bias) {
   constexpr int N = E * RG_LANES;
   constexpr bool weights_only = WO;
   const int gl = threadIdx.x & 7, j0 = gl * E;
@@ -405,7 +426,7 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     const bool active = ray_raw < B;
     const long long ray = active ? ray_raw : B - 1;
     RgRay<E> r;
-    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding);
+    rg_fetch<E>(r, rgb_or_raw, density, t_vals, dirs, ray, N, gl, head_mode, !weights_only, rgb_padding, head_bias);
     float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f, gd = 0.f;
     if (!weights_only) {
       if (g_rgb) { gr = __ldg(g_rgb + ray * 3); gg = __ldg(g_rgb + ray * 3 + 1); gb = __ldg(g_rgb + ray * 3 + 2); }
@@ -453,12 +474,15 @@ composite_bwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
       gs[i] = g_dd * r.delta[i];
     }
     if (!active) continue;
-    if (head_mode == 1) {
+    if (head_mode >= 1) {
       float4* out = reinterpret_cast<float4*>(g_raw) + ray * N + j0;
 #pragma unroll
-      for (int i = 0; i < E; ++i)
-        out[i] = make_float4(gs[i] * sigmoid_f(r.aux[i] + density_bias), r.w[i] * gr * cscale, r.w[i] * gg * cscale,
-                             r.w[i] * gb * cscale);
+      for (int i = 0; i < E; ++i) {
+        float4 gy = make_float4(gs[i] * sigmoid_f(r.aux[i] + density_bias), r.w[i] * gr * cscale, r.w[i] * gg * cscale,
+                                r.w[i] * gb * cscale);
+        if (head_mode == 2) gy = head_sigmoid_bwd(gy, r.aux[i], r.c[i][0], r.c[i][1], r.c[i][2], cscale, rgb_padding);
+        out[i] = gy;
+      }
     } else {
       if (g_density) {
         if (density_mode == 1) {
@@ -567,25 +591,26 @@ int mip360_composite_fwd(const float* rgb_or_raw, const float* density, const fl
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
                          float* distance, float* acc, float* weights, mip360_stream_t stream) {
   return mip360_composite_fwd_s(rgb_or_raw, density, t_vals, dirs, B, N, head_mode, density_bias, rgb_padding, white_bkgd,
-                                comp_rgb, distance, acc, weights, nullptr, nullptr, nullptr, nullptr, stream);
+                                comp_rgb, distance, acc, weights, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                            int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd, float* comp_rgb,
                            float* distance, float* acc, float* weights, const float* near, const float* far,
-                           float* s_vals, float* t_shift, mip360_stream_t stream) {
+                           float* s_vals, float* t_shift, const float* head_bias, mip360_stream_t stream) {
   MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs && comp_rgb && distance && acc), "composite_fwd: null pointer");
+  MIP_REQUIRE(head_mode >= 0 && head_mode <= 2 && (head_mode != 2 || head_bias), "composite_fwd: head_mode %d (2 needs head_bias)", head_mode);
   MIP_REQUIRE(B <= 0 || !s_vals || (near && far), "composite_fwd: s_vals needs near and far");
-  MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_fwd: density missing");
+  MIP_REQUIRE(B <= 0 || (head_mode >= 1 || density), "composite_fwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_fwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_fwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
-                         rgb_padding, white_bkgd, comp_rgb, distance, acc, weights, near, far, s_vals, t_shift);
+                         rgb_padding, white_bkgd, comp_rgb, distance, acc, weights, near, far, s_vals, t_shift, head_bias);
   else
     CP_GENERIC(composite_fwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, comp_rgb,
-        distance, acc, weights, near, far, s_vals, t_shift);
+        distance, acc, weights, near, far, s_vals, t_shift, head_bias);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -593,18 +618,19 @@ int mip360_composite_fwd_s(const float* rgb_or_raw, const float* density, const 
 int mip360_composite_bwd(const float* rgb_or_raw, const float* density, const float* t_vals, const float* dirs, int B,
                          int N, int head_mode, float density_bias, float rgb_padding, int white_bkgd,
                          const float* g_rgb, const float* g_acc, const float* g_dist, const float* g_w, float* g_rgb_in,
-                         float* g_density, float* g_raw, mip360_stream_t stream) {
+                         float* g_density, float* g_raw, const float* head_bias, mip360_stream_t stream) {
   MIP_REQUIRE(B <= 0 || (rgb_or_raw && t_vals && dirs), "composite_bwd: null pointer");
-  MIP_REQUIRE(B <= 0 || (head_mode == 1 || density), "composite_bwd: density missing");
+  MIP_REQUIRE(head_mode >= 0 && head_mode <= 2 && (head_mode != 2 || head_bias), "composite_bwd: head_mode %d (2 needs head_bias)", head_mode);
+  MIP_REQUIRE(B <= 0 || (head_mode >= 1 || density), "composite_bwd: density missing");
   MIP_REQUIRE(N >= 1 && N <= MIP360_MAX_SAMPLES, "composite_bwd: N=%d outside [1,%d]", N, MIP360_MAX_SAMPLES);
   if (B <= 0) return MIP360_OK;
   if (rg_supported_host(N))
     launch_composite_bwd<false>(N, B, (cudaStream_t)stream, rgb_or_raw, density, t_vals, dirs, B, head_mode, 0, 0, density_bias,
-                         rgb_padding, white_bkgd, g_rgb, g_acc, g_dist, g_w, g_rgb_in, g_density, g_raw);
+                         rgb_padding, white_bkgd, g_rgb, g_acc, g_dist, g_w, g_rgb_in, g_density, g_raw, head_bias);
   else
     CP_GENERIC(composite_bwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rgb_or_raw, density, t_vals, dirs, B, N, head_mode, 0, 0, density_bias, rgb_padding, white_bkgd, g_rgb, g_acc,
-        g_dist, g_w, g_rgb_in, g_density, g_raw);
+        g_dist, g_w, g_rgb_in, g_density, g_raw, head_bias);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -617,11 +643,11 @@ int mip360_density_to_weight_fwd(const float* density, const float* t_vals, cons
   if (rg_supported_host(N))
     launch_composite_fwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
                          density_bias, 0.f, 0, (float*)nullptr, (float*)nullptr, (float*)nullptr, weights,
-                         (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr);
+                         (const float*)nullptr, (const float*)nullptr, (float*)nullptr, (float*)nullptr, (const float*)nullptr);
   else
     CP_GENERIC(composite_fwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr,
-        weights, nullptr, nullptr, nullptr, nullptr);
+        weights, nullptr, nullptr, nullptr, nullptr, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }
@@ -635,11 +661,11 @@ int mip360_density_to_weight_bwd(const float* density, const float* t_vals, cons
   if (rg_supported_host(N))
     launch_composite_bwd<true>(N, B, (cudaStream_t)stream, (const float*)nullptr, density, t_vals, dirs, B, 0, 1, density_mode,
                          density_bias, 0.f, 0, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, g_w,
-                         (float*)nullptr, g_density, (float*)nullptr);
+                         (float*)nullptr, g_density, (float*)nullptr, (const float*)nullptr);
   else
     CP_GENERIC(composite_bwd_kernel, N)<<<ray_grid(B, CP_WARPS), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         nullptr, density, t_vals, dirs, B, N, 0, 1, density_mode, density_bias, 0.f, 0, nullptr, nullptr, nullptr, g_w,
-        nullptr, g_density, nullptr);
+        nullptr, g_density, nullptr, nullptr);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -22,7 +22,7 @@ constexpr int BK = 64;    // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
-enum { EPI_FWD = 0, EPI_DGRAD = 1 };
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_FWD_HEAD = 2 /* forward with the head folded into the epilogue */ };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_SIGMOID_FAST = 3 /* internal: bf16-only outputs */ };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile;
@@ -57,6 +57,12 @@ struct LinearParams {
   float* out_f32;          // [M, n_valid] or null
   int M, N, K, act, n_valid;
   int packed_epi;          // packed fp32x2 / bf16x2 epilogue arithmetic (same results, about half the instructions)
+  // Head fused into this (the last trunk) layer, model.py:150-158,180-181: head_out[row, 0..3] += sum over this tile's
+  // columns of act(...)[row, col] * head_w4[col, 0..3] (fp32 [N, 4], column-interleaved head weights, bias excluded).
+  // The 64-column head GEMM and its 2 GB read of the trunk output disappear; with out_bf16 == null (inference) the
+  // trunk output is never written either.
+  const float* head_w4;
+  float* head_out;
 };
 
 // 32 accumulator columns of one row: + bias (broadcast reads from shared memory), activation
@@ -222,6 +228,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_y,
               const LinearParams p) {
   using Cfg = LinearCfg<BN, CG, OCC>;
+  constexpr bool IS_FWD = EPI == EPI_FWD || EPI == EPI_FWD_HEAD;
+  constexpr bool HEAD = EPI == EPI_FWD_HEAD;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
@@ -345,7 +353,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     for (int tile = unit; tile < total_tiles; tile += nunits) {
       const int m0 = (tile / tiles_n) * (BM * CG) + rank * BM, n0 = (tile % tiles_n) * BN;
       const int row = m0 + q * 32 + lane;
-      if (EPI == EPI_FWD && n0 != bias_n0) {
+      if (IS_FWD && n0 != bias_n0) {
         // bias tile into shared memory (read back as broadcasts).  With gridDim.x a multiple of the number
         // of column tiles every CTA keeps the same column block, so this runs once per kernel.
         if (bias_n0 >= 0) epi_bar_sync();  // everyone has finished reading the previous tile's bias
@@ -358,7 +366,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (EPI == EPI_FWD && !tma_out) {
+      float hacc[4] = {0.f, 0.f, 0.f, 0.f};  // fused head: this row's partial dot products over the tile's columns
+      constexpr bool fused_head = HEAD;
+      if (IS_FWD && !tma_out && !fused_head) {
         // fp32-only output = an MLP head: n_valid <= 8 real columns in the first column tile; nothing else of the
         // accumulator is read, no activation is evaluated on padding
         if (n0 == 0) {
@@ -409,11 +419,32 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           uint32_t v[32];
           tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
           tmem_ld_wait();
-          if (EPI == EPI_FWD && p.act == ACT_RELU && !p.out_f32 && p.packed_epi) {
+          if (fused_head) {
+            // activation in fp32, then 4 FMAs per column against the head weights (uniform 16-byte loads: every lane
+            // of the warp reads the same address, one L1 transaction per load)
+            float x[32];
+            const uint32_t bsm = bias_smem + (jj * 64 + h * 32) * 4u;
+            if (p.act == ACT_RELU) fwd_math<ACT_RELU>(v, bsm, x);
+            else if (p.act == ACT_SIGMOID || p.act == ACT_SIGMOID_FAST) fwd_math<ACT_SIGMOID_FAST>(v, bsm, x);
+            else fwd_math<ACT_NONE>(v, bsm, x);
+            const float4* w4 = reinterpret_cast<const float4*>(p.head_w4) + n0 + jj * 64 + h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 w = __ldg(w4 + i);
+              hacc[0] = fmaf(x[i], w.x, hacc[0]);
+              hacc[1] = fmaf(x[i], w.y, hacc[1]);
+              hacc[2] = fmaf(x[i], w.z, hacc[2]);
+              hacc[3] = fmaf(x[i], w.w, hacc[3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[16 * h + i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+            continue;
+          }
+          if (IS_FWD && p.act == ACT_RELU && !p.out_f32 && p.packed_epi) {
             fwd_relu_packed(v, bias_smem + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
             continue;
           }
-          if (EPI == EPI_FWD && p.act == ACT_SIGMOID_FAST && p.packed_epi) {  // (bf16-only output by construction)
+          if (IS_FWD && p.act == ACT_SIGMOID_FAST && p.packed_epi) {  // (bf16-only output by construction)
             fwd_sigmoid_fast_packed(v, bias_smem + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
             continue;
           }
@@ -426,7 +457,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             continue;
           }
           float x[32];
-          if (EPI == EPI_FWD) {
+          if (IS_FWD) {
             const uint32_t bsm = bias_smem + (jj * 64 + h * 32) * 4u;
             if (p.act == ACT_RELU) fwd_math<ACT_RELU>(v, bsm, x);
             else if (p.act == ACT_SIGMOID) fwd_math<ACT_SIGMOID>(v, bsm, x);
@@ -478,6 +509,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         bi = nbi;
         if (bi == 0) bphase ^= 1u;
       }
+      if (fused_head && row < p.M) red_add_v4(p.head_out + (size_t)row * 4, hacc[0], hacc[1], hacc[2], hacc[3]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -768,6 +800,8 @@ adamw_pack_kernel(const mip360_pack_entry* __restrict__ entries, int n_entries, 
     const uint16_t bits = *reinterpret_cast<const uint16_t*>(&b);
     E.Wb[(long long)n * E.k_pad + k] = bits;
     tile[r][tx] = bits;
+    // head weights once more as fp32 [k_pad, 4] (the bf16-rounded values, column-interleaved) for the fused-head epilogue
+    if (E.w4 && n < 4) E.w4[(long long)k * 4 + n] = __bfloat162float(b);
   }
   __syncthreads();
   if (E.Wt) {
@@ -943,6 +977,15 @@ int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, i
   const int act_k = (act == ACT_SIGMOID && !out_f32) ? ACT_SIGMOID_FAST : act;
   LinearParams p{bias, out_bf16, out_f32, M, N, K, act_k, n_valid, option(OPT_PACKED_EPILOGUE) ? 1 : 0};
   return dispatch_linear<EPI_FWD>(X, W, nullptr, p, (cudaStream_t)stream);
+}
+
+int mip360_linear_fwd_head(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
+                           uint16_t* out_bf16, const float* head_w4, float* head_out, mip360_stream_t stream) {
+  MIP_REQUIRE(X && W && bias && head_w4 && head_out, "linear_fwd_head: null pointer");
+  MIP_REQUIRE(M > 0 && N > 0 && K > 0 && K % BK == 0, "linear_fwd_head: bad shape M=%d N=%d K=%d (K %% 64 != 0?)", M, N, K);
+  MIP_REQUIRE(act >= 0 && act <= 2, "linear_fwd_head: act=%d", act);
+  LinearParams p{bias, out_bf16, nullptr, M, N, K, act == ACT_SIGMOID ? ACT_SIGMOID_FAST : act, 0, 0, head_w4, head_out};
+  return dispatch_linear<EPI_FWD_HEAD>(X, W, nullptr, p, (cudaStream_t)stream);
 }
 
 int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,

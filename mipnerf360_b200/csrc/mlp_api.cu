@@ -36,6 +36,32 @@ int mip360_mlp_fwd(const uint16_t* x, int M, const mip360_layer* trunk, int n_tr
   return mip360_linear_fwd(h, head->W, head->bias, M, 64, head->k_pad, head->act, nullptr, out, n_valid, stream);
 }
 
+int mip360_mlp_fwd_fused_head(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const float* head_w4,
+                              uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream) {
+  MIP_REQUIRE(trunk && n_trunk >= 1 && n_trunk <= 32 && head_w4, "mlp_fwd_fused_head: bad layer table");
+  MIP_REQUIRE(acts && out && (n_act_bufs == n_trunk || n_act_bufs == 2), "mlp_fwd_fused_head: need %d (saved) or 2 (ping-pong) buffers", n_trunk);
+  if (M <= 0) return MIP360_OK;
+  MIP_REQUIRE(x, "mlp_fwd_fused_head: null input");
+  MIP_CUDA(cudaMemsetAsync(out, 0, (size_t)M * 4 * sizeof(float), (cudaStream_t)stream));
+  const uint16_t* h = x;
+  int rc;
+  for (int l = 0; l < n_trunk; ++l) {
+    MIP_REQUIRE(trunk[l].W && trunk[l].bias, "mlp_fwd_fused_head: layer %d has null weights", l);
+    uint16_t* y = acts[n_act_bufs == 2 ? (l & 1) : l];
+    if (l + 1 < n_trunk) {
+      MIP_REQUIRE(y, "mlp_fwd_fused_head: activation buffer %d is null", l);
+      rc = mip360_linear_fwd(h, trunk[l].W, trunk[l].bias, M, trunk[l].n_pad, trunk[l].k_pad, trunk[l].act, y, nullptr, 0, stream);
+    } else {
+      // inference (ping-pong buffers): nobody reads the last trunk activation, so it is not written
+      rc = mip360_linear_fwd_head(h, trunk[l].W, trunk[l].bias, M, trunk[l].n_pad, trunk[l].k_pad, trunk[l].act,
+                                  n_act_bufs == 2 ? nullptr : y, head_w4, out, stream);
+    }
+    if (rc != MIP360_OK) return rc;
+    h = y;
+  }
+  return MIP360_OK;
+}
+
 int mip360_mlp_bwd(const float* g_out, const float* out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
                    const mip360_layer* head, int n_valid, uint16_t* const* acts, float* const* dW, float* const* db,
                    uint16_t* dz_head, uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream) {

@@ -45,6 +45,10 @@ class PackedMLP:
         self.n_valid = sum(h.out_features for h in heads)
         if len(heads) > 2:
             raise ValueError("at most two head Linear modules can share the padded head")
+        # Fold the head into the epilogue of the last trunk layer (mip360_linear_fwd_head): the MLP then returns the head's
+        # PRE-activation sums without bias, and the consumer applies bias + head activation (ops.composite_heads with
+        # head_bias=).  Set by the owner of the MLP (nerf_net) when its consumer does that.
+        self.fuse_head = False
         self._key = None        # (data_ptr, version) of every parameter at the last refresh
         self._ptr_key = None    # data_ptr of every parameter the device table was built for
         self._packed = None
@@ -83,6 +87,7 @@ class PackedMLP:
                 torch.empty((k_pad, 64), device=dev, dtype=torch.bfloat16),
                 torch.empty(64, device=dev, dtype=torch.float32))
         self._packed = (layers, head)
+        self.head_w4 = torch.zeros((k_pad, 4), device=dev, dtype=torch.float32)  # rows 0..3 of the head, column-interleaved
         acts = [a for _, a in self.trunk]
         arr = (_lib.Layer * len(layers))()
         for i, ((W_, Wt_, b_), a) in enumerate(zip(layers, acts)):
@@ -106,6 +111,7 @@ class PackedMLP:
             e.K = lins[0].in_features
             e.n_pad, e.k_pad, e.tile_begin = Wb.shape[0], Wb.shape[1], tile
             e.Wb, e.Wt, e.bias = Wb.data_ptr(), Wt.data_ptr(), bias.data_ptr()
+            e.w4 = self.head_w4.data_ptr() if i == len(bufs) - 1 else None
             tile += (Wb.shape[0] // 32) * (Wb.shape[1] // 32)
         raw = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8)
         self._table = raw.to(layers[0][0].device)
@@ -140,6 +146,10 @@ class PackedMLP:
         self.packed()
         return self._cstructs
 
+    def head_bias(self):
+        """Padded fp32 head bias [64] (first n_valid entries real), refreshed with the operands."""
+        return self.packed()[1][2]
+
 
 class _MLPFunction(torch.autograd.Function):
     """x bf16 [M,64] -> head outputs fp32 [M, n_valid]; gradients for every weight and bias (fp32).
@@ -152,15 +162,36 @@ class _MLPFunction(torch.autograd.Function):
         layers, (Wh, Wht, bh) = mlp.packed()
         acts = [a for _, a in mlp.trunk]
         M, L = x.shape[0], len(layers)
+        fuse = mlp.fuse_head and mlp.n_valid == 4
         if _lib.PROFILE is not None:
             # instrumented runs (bench.py's per-kernel table): one C call per GEMM so that each launch is timed
             saved = [x]
             h = x
-            for (Wb, _, bias), act in zip(layers, acts):
-                h, _ = ops.linear_fwd(h, Wb, bias, act)
+            for l, ((Wb, _, bias), act) in enumerate(zip(layers, acts)):
+                if fuse and l == L - 1:
+                    out = torch.zeros((M, 4), device=x.device, dtype=torch.float32)
+                    h = ops.linear_fwd_head(h, Wb, bias, act, mlp.head_w4, out, want_bf16=need_grad)
+                else:
+                    h, _ = ops.linear_fwd(h, Wb, bias, act)
                 if need_grad:
                     saved.append(h)
-            _, out = ops.linear_fwd(h, Wh, bh, mlp.head_act, out_f32_cols=mlp.n_valid, want_bf16=False)
+            if not fuse:
+                _, out = ops.linear_fwd(h, Wh, bh, mlp.head_act, out_f32_cols=mlp.n_valid, want_bf16=False)
+        elif fuse:
+            # product path with the head folded into the last trunk layer: one C call, no head GEMM, and on inference
+            # passes no write of the last trunk activation either
+            trunk_arr, _ = mlp.cstructs()
+            if need_grad:
+                bufs = [torch.empty((M, Wb.shape[0]), device=x.device, dtype=torch.bfloat16) for Wb, _, _ in layers]
+            else:
+                wmax = max(Wb.shape[0] for Wb, _, _ in layers)
+                bufs = [torch.empty((M, wmax), device=x.device, dtype=torch.bfloat16) for _ in range(2)]
+            out = torch.empty((M, 4), device=x.device, dtype=torch.float32)
+            mlp.last_n_act_bufs = len(bufs)
+            ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+            _lib.call("mip360_mlp_fwd_fused_head", x.data_ptr(), M, trunk_arr, L, mlp.head_w4.data_ptr(), ptrs, len(bufs),
+                      out.data_ptr())
+            saved = [x] + bufs
         else:
             # product path: the whole MLP is one call into the C ABI (mip360_mlp_fwd)
             trunk_arr, head = mlp.cstructs()
@@ -178,6 +209,7 @@ class _MLPFunction(torch.autograd.Function):
         if need_grad:
             ctx.mlp = mlp
             ctx.acts = acts
+            ctx.fused = fuse
             ctx.save_for_backward(out, *saved)
         return out
 
@@ -225,11 +257,14 @@ class _MLPFunction(torch.autograd.Function):
             if mlp.grad_hook is not None:
                 mlp.grad_hook(l)
 
+        # fused head: `out` are pre-activation sums and g_out is already dL/d(pre-activation) (the consumer applied the
+        # head activation and its derivative), so the head gradient is packed without an activation derivative
+        head_act = ACT_NONE if ctx.fused else mlp.head_act
         per_layer = _lib.PROFILE is not None or (direct and mlp.grad_hook is not None)
         if per_layer:
             # one C call per GEMM: instrumented runs (bench.py's per-kernel table) and the data-parallel trainer,
             # which starts the all-reduce of a layer's gradients as soon as its wgrad has been enqueued
-            dzh = ops.head_grad_pack(g_out, out if mlp.head_act == ACT_SIGMOID else None, mlp.head_act)
+            dzh = ops.head_grad_pack(g_out, out if head_act == ACT_SIGMOID else None, head_act)
             ops.linear_wgrad(dzh, saved[L], dW=dWh, db=dbh)
             dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
             for l in range(L, 0, -1):  # trunk layer l-1 maps saved[l-1] -> saved[l]
@@ -247,6 +282,8 @@ class _MLPFunction(torch.autograd.Function):
             dW_ptrs = (ctypes.c_void_p * (L + 1))(*([t[0].data_ptr() for t in targets] + [dWh.data_ptr()]))
             db_ptrs = (ctypes.c_void_p * (L + 1))(*([t[1].data_ptr() for t in targets] + [dbh.data_ptr()]))
             g = ops.f32c(g_out)
+            if ctx.fused:  # the head activation derivative is already in g_out: pack it as is
+                head = _lib.Layer(head.W, head.Wt, head.bias, head.n_pad, head.k_pad, ACT_NONE)
             _lib.call("mip360_mlp_bwd", g.data_ptr(), out.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
                       ctypes.byref(head), mlp.n_valid, act_ptrs, dW_ptrs, db_ptrs, dzh.data_ptr(), dz0.data_ptr(),
                       dz1.data_ptr())

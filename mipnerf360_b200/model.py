@@ -154,6 +154,9 @@ class nerf_net(nn.Module):
         _kaiming_init(self)
         self.to(device)
         self._packed = _mlp.pack_nerf(self.model, self.final_density, self.final_color)
+        # final_density / final_color (model.py:150-158) ride in the epilogue of the last trunk GEMM; their bias and
+        # Sigmoid are applied by the compositing kernel
+        self._packed.fuse_head = True
 
     _norm_buffer = _norm_buffer
 
@@ -165,11 +168,13 @@ class nerf_net(nn.Module):
                              norm_sq=norm_sq)
         N = new_t.shape[1] - 1
         x = _encode(rays, new_t, self.viewdirs_encoding, self.contract_mode, self.batch_group, norm_sq)
-        raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 4] = (density head, colour head), post-sigmoid
-        # heads' activations, compositing and model.py:196's t_to_s in one launch
+        raw = _mlp.mlp_apply(self._packed, x)  # [B*N, 4] = (density head, colour head)
+        # heads' bias + Sigmoid (fused-head MLP: raw holds pre-activation sums), compositing and model.py:196's t_to_s
+        # in one launch
+        head_bias = self._packed.head_bias() if self._packed.fuse_head else None
         comp_rgb, distance, acc, weights, s_vals, t_shift = ops.composite_heads(
             raw.view(B, N, 4), new_t, rays.directions, self.density_bias, self.rgb_padding, self.white_bkgd,
-            near=rays.near, far=rays.far)
+            near=rays.near, far=rays.far, head_bias=head_bias)
         # model.py:193-196: stashed for the distillation / regularisation losses; the reference's t_vals comes
         # back shifted by +1e-6 because t_to_s -> g() adds eps in place (App. A4)
         self.fine_weights = weights

@@ -307,7 +307,8 @@ class _Composite(torch.autograd.Function):
     """intern/ray.py:155-191 (+ model.py:184-185 when head_mode=1)."""
 
     @staticmethod
-    def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd, s_out=None):
+    def forward(ctx, rgb_or_raw, density, t_vals, dirs, head_mode, density_bias, rgb_padding, white_bkgd, s_out=None,
+                head_bias=None):
         ctx.set_materialize_grads(False)  # unused outputs (distance, acc in training) arrive as None, not zeros
         B, N = t_vals.shape[0], t_vals.shape[1] - 1
         comp, dist, acc = _empty((B, 3), t_vals), _empty((B,), t_vals), _empty((B,), t_vals)
@@ -315,7 +316,8 @@ class _Composite(torch.autograd.Function):
         near, far, s_vals, t_shift = s_out if s_out is not None else (None, None, None, None)
         call("mip360_composite_fwd_s", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
              density_bias, rgb_padding, int(white_bkgd), ptr(comp), ptr(dist), ptr(acc), ptr(w), ptr(near), ptr(far),
-             ptr(s_vals), ptr(t_shift))
+             ptr(s_vals), ptr(t_shift), ptr(head_bias))
+        ctx.head_bias = head_bias
         ctx.save_for_backward(rgb_or_raw, density, t_vals, dirs)
         ctx.cfg = (head_mode, density_bias, rgb_padding, int(white_bkgd))
         return comp, dist, acc, w
@@ -329,7 +331,7 @@ class _Composite(torch.autograd.Function):
         g_acc = f32c(g_acc) if g_acc is not None else None
         g_dist = f32c(g_dist) if g_dist is not None else None
         g_w = f32c(g_w) if g_w is not None else None
-        if head_mode == 1:
+        if head_mode >= 1:
             g_raw = torch.empty_like(rgb_or_raw)
             g_rgb_in = g_density = None
         else:
@@ -337,10 +339,10 @@ class _Composite(torch.autograd.Function):
             g_rgb_in, g_density = torch.empty_like(rgb_or_raw), torch.empty_like(density)
         call("mip360_composite_bwd", ptr(rgb_or_raw), ptr(density), ptr(t_vals), ptr(dirs), B, N, head_mode,
              density_bias, rgb_padding, white, ptr(g_comp), ptr(g_acc), ptr(g_dist), ptr(g_w), ptr(g_rgb_in),
-             ptr(g_density), ptr(g_raw))
-        if head_mode == 1:
-            return g_raw, None, None, None, None, None, None, None, None
-        return g_rgb_in, g_density, None, None, None, None, None, None, None
+             ptr(g_density), ptr(g_raw), ptr(ctx.head_bias))
+        if head_mode >= 1:
+            return g_raw, None, None, None, None, None, None, None, None, None
+        return g_rgb_in, g_density, None, None, None, None, None, None, None, None
 
 
 def _no_grad_inputs(who, **tensors):
@@ -360,19 +362,26 @@ def composite(rgb, density, t_vals, dirs, white_bkgd):
     return _Composite.apply(rgb, density, t_vals, dirs, 0, 0.0, 0.0, bool(white_bkgd))
 
 
-def composite_heads(raw, t_vals, dirs, density_bias, rgb_padding, white_bkgd, near=None, far=None):
-    """model.py:184-186 fused: raw [B,N,4] = (density head, colour head) post-sigmoid outputs of the MLP.
+def composite_heads(raw, t_vals, dirs, density_bias, rgb_padding, white_bkgd, near=None, far=None, head_bias=None):
+    """model.py:184-186 fused: raw [B,N,4] = (density head, colour head) post-sigmoid outputs of the MLP — or, with
+    head_bias [>=4] (device), the heads' pre-activation sums without bias as the fused-head MLP produces them
+    (mlp.PackedMLP.fuse_head): bias and Sigmoid (model.py:150-158) are then applied here.
     With near / far the same launch also produces model.py:196's s_vals = t_to_s(t_vals, near, far) and the shifted
     t_vals the reference returns (App. A4): -> (comp_rgb, distance, acc, weights, s_vals, t_shift)."""
     raw, t_vals, dirs = f32c(raw), f32c(t_vals), f32c(dirs)
     check_cuda(raw, t_vals, dirs)
+    mode = 1
+    if head_bias is not None:
+        check_cuda(head_bias)
+        mode, head_bias = 2, head_bias.detach()
     if near is None:
-        return _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd))
+        return _Composite.apply(raw, None, t_vals, dirs, mode, float(density_bias), float(rgb_padding), bool(white_bkgd),
+                                None, head_bias)
     near, far = f32c(near), f32c(far)
     check_cuda(near, far)
     s_vals, t_shift = torch.empty_like(t_vals), torch.empty_like(t_vals)
-    out = _Composite.apply(raw, None, t_vals, dirs, 1, float(density_bias), float(rgb_padding), bool(white_bkgd),
-                           (near, far, s_vals, t_shift))
+    out = _Composite.apply(raw, None, t_vals, dirs, mode, float(density_bias), float(rgb_padding), bool(white_bkgd),
+                           (near, far, s_vals, t_shift), head_bias)
     return out + (s_vals, t_shift)
 
 
@@ -564,6 +573,16 @@ def linear_fwd(x, Wb, bias, act, out_f32_cols=0, want_bf16=True):
     yf = torch.empty((M, out_f32_cols), device=x.device, dtype=torch.float32) if out_f32_cols else None
     call("mip360_linear_fwd", ptr(x), ptr(Wb), ptr(bias), M, N, K, act, ptr(y), ptr(yf), out_f32_cols)
     return y, yf
+
+
+def linear_fwd_head(x, Wb, bias, act, head_w4, head_out, want_bf16=True):
+    """The last trunk layer with the head folded into its epilogue: y = act(x Wb^T + bias) (bf16, optional) and
+    head_out [M,4] += y head_w4 (fp32, accumulated: zero it first)."""
+    M, K = x.shape
+    N = Wb.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    call("mip360_linear_fwd_head", ptr(x), ptr(Wb), ptr(bias), M, N, K, act, ptr(y), ptr(head_w4), ptr(head_out))
+    return y
 
 
 def linear_dgrad(dY, Wt, y_prev, act, out=None):

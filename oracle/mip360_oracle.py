@@ -119,6 +119,24 @@ def gaussian_contract(mean, cov, norm_sq=None):
     return mean_c, cov_c
 
 
+def gaussian_contract_literal(mean, cov):
+    """intern/parameterization.py:64-83 AS WRITTEN: one torch.autograd.functional.jacobian call per sample in a double
+    Python loop (the reference's dominant cost, SURVEY §6: 0.15-0.18 ms per call).  Used to time the literal algorithm
+    (bench.py's CPU baseline) and to pin the closed form of `gaussian_contract` against it; O(B*N) Python iterations."""
+    from torch.autograd.functional import jacobian
+    mean = contract(mean)
+    jf = torch.zeros((mean.shape[0], mean.shape[1], 3, 3), dtype=mean.dtype)
+    for b in range(mean.shape[0]):
+        for n in range(mean.shape[1]):
+            jf[b][n] = jacobian(contract, mean[b][n])
+    cov = torch.matmul(jf, cov)
+    cov = torch.matmul(cov, jf.transpose(2, 3))
+    return mean, cov
+
+
+LITERAL_CONTRACT = False  # set by bench.py to time the reference's per-sample Jacobian loop instead of the closed form
+
+
 def frustum_moments(t0, t1, radii, stable=True):
     """intern/parameterization.py:100-113: the stable formula of the mip-NeRF paper, or the original one."""
     if not stable:
@@ -139,6 +157,9 @@ def conical_frustum_to_gaussian(d, t0, t1, radii, norm_sq=None, stable=True):
     gaussian_contract: a [B,N,3] diagonal cannot be multiplied by the [B,N,3,3] Jacobians)."""
     t_mean, t_var, r_var = frustum_moments(t0, t1, radii, stable)
     mean, cov = gaussian_to_xyz(d, t_mean, t_var, r_var)
+    if LITERAL_CONTRACT and norm_sq is None:
+        with torch.no_grad():  # Jf is filled from detached jacobian() results in the reference too (:76-79)
+            return gaussian_contract_literal(mean, cov)
     return gaussian_contract(mean, cov, norm_sq)
 
 

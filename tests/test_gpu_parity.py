@@ -507,7 +507,8 @@ def test_default_model_vs_oracle():
     close(new_t + 1e-6, t_r, rtol=1e-5, atol=2e-5)
     x = ops.cast_ipe(new_t, rays.origins, rays.directions, rays.radii, vd, want_x=True)["x"]
     raw = MLP.mlp_apply(m.nerf_net._packed, x)
-    rgb, dist, acc, w = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions, -1, 0.001, False)
+    rgb, dist, acc, w = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions, -1, 0.001, False,
+                                           head_bias=m.nerf_net._packed.head_bias())
     s, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
     close(rgb, rgb_r, rtol=2e-2, atol=1e-2, msg="rgb")
     close(acc, acc_r, rtol=2e-2, atol=1e-2)

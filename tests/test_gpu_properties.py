@@ -288,7 +288,8 @@ def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu():
     torch.testing.assert_close(new_t + 1e-6, t_r, rtol=1e-4, atol=1e-4)
     x = ops.cast_ipe(new_t, rays.origins, rays.directions, rays.radii, vd, want_x=True)["x"]
     raw = MLP.mlp_apply(m.nerf_net._packed, x)
-    rgb, dist, acc, w = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions, -1, 0.001, False)
+    rgb, dist, acc, w = ops.composite_heads(raw.view(B, N, 4), new_t, rays.directions, -1, 0.001, False,
+                                           head_bias=m.nerf_net._packed.head_bias())
     s, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
     for name, a, b in (("w_hat", w_hat, w_hat_r), ("rgb", rgb, rgb_r), ("acc", acc, acc_r), ("w", w, w_r)):
         err = (a.detach() - b).abs()

@@ -474,7 +474,7 @@ def test_in_kernel_random_draws_match_the_restated_generator(ops, B, N):
     assert abs(float(nsq) - ref_n) <= 1e-6 * ref_n
     pre = ops.frustum_norm_sq(t.data_ptr(), t.data_ptr() + 4, N + 1, d.to(dev), B, N)
     # the pre-pass kernels: same per-sample fp32 arithmetic for N in {32,64,128}; the generic one squares in fp64
-    assert abs(float(nsq) - float(pre)) <= (1e-12 if N in (32, 64, 128) else 1e-8) * float(pre)
+    assert abs(float(nsq) - float(pre)) <= (1e-12 if N in (32, 64, 128) else 1e-7) * float(pre)
     # resampling: jitter = u01 * (1/M - eps), the way torch's uniform_(0, 1/M - eps) scales its draw
     w = torch.rand(B, N, generator=g) ** 2 * 0.2
     jit = torch.from_numpy(philox.uniform(seed, stream_id + 1, 5, (B, N + 1))) * torch.tensor(ops.jitter_scale(N + 1))
@@ -488,7 +488,7 @@ def test_in_kernel_random_draws_match_the_restated_generator(ops, B, N):
     # bit-exact (test_resample_vs_oracle, two-stage API).
     close(new_t, ref_t, rtol=1e-4, atol=2e-5)
     pre2 = ops.frustum_norm_sq(new_t.data_ptr(), new_t.data_ptr() + 4, N + 1, d.to(dev), B, N)
-    assert abs(float(nsq2) - float(pre2)) <= (1e-12 if N in (32, 64, 128) else 1e-8) * float(pre2)
+    assert abs(float(nsq2) - float(pre2)) <= (1e-12 if N in (32, 64, 128) else 1e-7) * float(pre2)
     # another replay epoch / call site gives other numbers; the default path follows torch.manual_seed
     epoch2 = torch.tensor([6], dtype=torch.int64, device=dev)
     assert not torch.equal(t, ops.level0_t_vals(near.to(dev), far.to(dev), N, True, rng=(seed, stream_id, epoch2)))
@@ -644,3 +644,57 @@ def test_other_viewdir_degrees_vs_literal_reference_and_oracle(golden2, ops):
     gk = "nerf_net.model.0.weight"
     gd = dict(m.named_parameters())[gk].grad.cpu()
     assert float((gd - params[gk].grad).norm() / params[gk].grad.norm()) < 5e-2
+
+
+def test_fused_head_equals_separate_head_gemm():
+    """nerf_net with final_density / final_color folded into the last trunk GEMM's epilogue (default) against the same
+    net with the separate 64-column head GEMM: outputs, losses and every gradient; inference skips the last trunk
+    activation; the profiled (one call per GEMM) path takes the same route."""
+    from mipnerf360_b200 import _lib
+    from mipnerf360_b200.intern.loss import Loss_dist, Loss_nerf
+    from mipnerf360_b200.model import mipNeRF360
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(12)
+    B = 300  # 19200 samples: several 256-row tiles and a ragged last one
+    o, d = torch.randn(B, 3, generator=g), torch.randn(B, 3, generator=g)
+    rays = O.Rays(*[x.to(dev) for x in (o, d, d / d.norm(dim=-1, keepdim=True), torch.full((B, 1), 1e-3),
+                                        torch.full((B, 1), 0.1), torch.full((B, 1), 10.0))])
+    pixels = torch.rand(B, 3, generator=g).to(dev)
+    for widths in ((256, 1024), (64, 128)):
+        torch.manual_seed(5)
+        m = mipNeRF360(randomized=False, num_samples=64, hidden_proposal=widths[0], hidden_nerf=widths[1], device=dev)
+        outs = {}
+        for fuse in (True, False):
+            m.nerf_net._packed.fuse_head = fuse
+            m.zero_grad()
+            with torch.no_grad():
+                t_hat, w_hat = m.prop_net(rays)
+            rgb, dist, acc, t, w, s = m.nerf_net(rays, t_hat, w_hat)
+            loss = Loss_nerf(rgb, pixels)[0] + 0.01 * Loss_dist(s, w)
+            loss.backward()
+            outs[fuse] = dict(rgb=rgb.detach(), acc=acc.detach(), w=w.detach(), loss=loss.detach(),
+                              grads={k: p.grad.clone() for k, p in m.nerf_net.named_parameters()})
+            with torch.no_grad():
+                inf = m.nerf_net(rays, t_hat, w_hat)[0]
+            assert m.nerf_net._packed.last_n_act_bufs == 2
+            close(inf, rgb, rtol=1e-6, atol=1e-6)  # the inference route (no trunk activation written) = the training route
+        a, b = outs[True], outs[False]
+        # the fused dot uses the fp32 trunk activations, the head GEMM their bf16 roundings: agreement well inside bf16
+        close(a["rgb"], b["rgb"], rtol=2e-3, atol=2e-3, msg="rgb")
+        close(a["w"], b["w"], rtol=2e-3, atol=1e-4, msg="weights")
+        close(a["loss"], b["loss"], rtol=2e-3, atol=1e-3)
+        for k in a["grads"]:
+            rel = float((a["grads"][k] - b["grads"][k]).norm() / b["grads"][k].norm().clamp_min(1e-20))
+            assert rel < 2e-2, (widths, k, rel)
+        # instrumented path (bench.py's per-kernel table)
+        m.nerf_net._packed.fuse_head = True
+        _lib.PROFILE = []
+        try:
+            with torch.no_grad():
+                t_hat, w_hat = m.prop_net(rays)
+                prof_rgb = m.nerf_net(rays, t_hat, w_hat)[0]
+        finally:
+            names = [n for n, *_ in _lib.PROFILE]
+            _lib.PROFILE = None
+        assert "mip360_linear_fwd_head" in names
+        close(prof_rgb, a["rgb"], rtol=1e-6, atol=1e-6)

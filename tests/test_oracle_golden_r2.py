@@ -121,3 +121,18 @@ def test_more_than_128_samples(golden2):
     close(O.Loss_prop(c["t_fine"], c["w_fine"], c["t_coarse"], c["w_coarse"]), c["Loss_prop"], rtol=1e-5)
     c = golden2.case("n150_distortion")
     close(O.loss_dist(c["s_vals"], c["weights"]), c["loss"], rtol=2e-5)
+
+
+def test_literal_contract_loop_equals_closed_form():
+    """The per-sample autograd-Jacobian loop of parameterization.py:64-83 (restated as written) against the closed form
+    the oracle and the kernels use, including samples whose Jacobian is not the identity."""
+    g = torch.Generator().manual_seed(0)
+    mean = torch.randn(3, 5, 3, generator=g) * 0.4
+    mean[0, 0] = torch.tensor([30.0, -10.0, 5.0])  # dominates the global norm: stays outside the unit ball after scaling
+    A = torch.randn(3, 5, 3, 3, generator=g) * 0.2
+    cov = A @ A.transpose(-1, -2)
+    m_lit, c_lit = O.gaussian_contract_literal(mean.clone(), cov.clone())
+    m_cf, c_cf = O.gaussian_contract(mean, cov)
+    assert (m_cf.norm(dim=-1) > 1).any()
+    close(m_cf, m_lit, rtol=0, atol=0)
+    cov_close(c_cf, c_lit, rel=3e-6)
