@@ -256,6 +256,12 @@ int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, i
  * head_mode 2). */
 int mip360_linear_fwd_head(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,
                            uint16_t* out_bf16, const float* head_w4, float* head_out, mip360_stream_t stream);
+/* Backward of a fused head in one pass over the saved trunk output Y [M,N] (bf16; act = the trunk layer's activation):
+ * g [M,4] = dL/d(head pre-activation), head_w4 [N,4] as above.  Writes dZ [M,N] bf16 = (g head_w4^T) .* act'(Y), the
+ * gradient entering the last trunk layer, and ACCUMULATES dWh[h, c] += sum_r g[r,h] Y[r,c] (row pitch ldw floats) and
+ * dbh[h] += sum_r g[r,h] (may be NULL).  Replaces mip360_head_grad_pack + the head's wgrad and dgrad GEMMs. */
+int mip360_head_bwd(const float* g, const float* head_w4, const uint16_t* Y, int M, int N, int act, uint16_t* dZ,
+                    float* dWh, int ldw, float* dbh, mip360_stream_t stream);
 int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,
                         uint16_t* dX, mip360_stream_t stream);
 int mip360_linear_wgrad(const uint16_t* dY, const uint16_t* X, int M, int N, int K, float* dW, float* db,
@@ -283,6 +289,11 @@ int mip360_mlp_fwd(const uint16_t* x, int M, const mip360_layer* trunk, int n_tr
  * activation is not written at all. */
 int mip360_mlp_fwd_fused_head(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const float* head_w4,
                               uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream);
+/* Backward of mip360_mlp_fwd_fused_head: g_out [M,4] = dL/d(out) (pre-activation sums), mip360_head_bwd for the head,
+ * then the trunk as in mip360_mlp_bwd.  dW[n_trunk] is the head's [64, k_pad] gradient (rows 0..3 written), db[n_trunk] [64]. */
+int mip360_mlp_bwd_fused_head(const float* g_out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
+                              const float* head_w4, uint16_t* const* acts, float* const* dW, float* const* db,
+                              uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream);
 int mip360_mlp_bwd(const float* g_out, const float* out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
                    const mip360_layer* head, int n_valid, uint16_t* const* acts, float* const* dW, float* const* db,
                    uint16_t* dz_head, uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream);

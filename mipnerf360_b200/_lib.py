@@ -61,11 +61,13 @@ SIGNATURES = {
     "mip360_interlevel_bwd": [P, P, P, c_int, c_int, c_int, c_float, P, P, P],
     "mip360_linear_fwd": [P, P, P, c_int, c_int, c_int, c_int, P, P, c_int, P],
     "mip360_linear_fwd_head": [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
+    "mip360_head_bwd": [P, P, P, c_int, c_int, c_int, P, P, c_int, P, P],
     "mip360_linear_dgrad": [P, P, P, c_int, c_int, c_int, c_int, P, P],
     "mip360_linear_wgrad": [P, P, c_int, c_int, c_int, P, P, P],
     "mip360_cast_weight": [P, c_int, c_int, c_int, c_int, P, P, P],
     "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
     "mip360_mlp_fwd_fused_head": [P, c_int, P, c_int, P, P, c_int, P, P],
+    "mip360_mlp_bwd_fused_head": [P, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_generate_rays": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, P, P, P, P, P, P, P],
     "mip360_generate_rays_range": [P, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_longlong,

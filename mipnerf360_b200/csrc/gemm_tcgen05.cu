@@ -48,6 +48,9 @@ struct LinearCfg {
   static constexpr int EPI_BYTES = NBOX * 4 * EPI_BOX_BYTES + 1024 /* bias tile: up to 256 floats */;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;  static_assert(SMEM_BYTES <= 232448 / OCC, "exceeds the shared memory available per CTA at this occupancy");
+  // fused head (EPI_FWD_HEAD): the BN x 4 fp32 head weights of the CTA's column tile, after the barriers, when they fit
+  static constexpr int HEAD_BYTES = BN * 16;
+  static constexpr bool HEAD_SMEM = SMEM_BYTES + HEAD_BYTES <= 232448 / OCC;
   static_assert(TMEM_COLS * OCC <= 512, "tensor memory oversubscribed");
 };
 
@@ -181,6 +184,64 @@ __device__ __forceinline__ void fwd_sigmoid_fast_packed(const uint32_t (&v)[32],
     pk[2 * i + 1] = pack_bf16x2(__uint_as_float(r2), __uint_as_float(r3));
   }
 }
+//   trunk Sigmoid + fused head: the same packed Sigmoid, then per column two fp32x2 FMAs of (y, y) against the column's four
+//   head weights (one 16-byte shared-memory broadcast load) into the row's two accumulator pairs
+__device__ __forceinline__ void fwd_sigmoid_fast_head_packed(const uint32_t (&v)[32], uint32_t bias_addr, uint32_t w4_addr,
+                                                             uint32_t* pk, uint64_t& acc01, uint64_t& acc23) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 bb;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bb.x), "=r"(bb.y), "=r"(bb.z), "=r"(bb.w) : "r"(bias_addr + 16u * i));
+    uint32_t r0, r1, r2, r3;
+    asm("{\n"
+        ".reg .b64 a, b, c, hh;\n"
+        ".reg .f32 t0, t1;\n"
+        "mov.b64 hh, {%12, %12};\n"
+        "mov.b64 a, {%4, %5};\n"
+        "mov.b64 b, {%8, %9};\n"
+        "add.rn.f32x2 c, a, b;\n"
+        "mul.rn.f32x2 c, c, hh;\n"
+        "mov.b64 {t0, t1}, c;\n"
+        "tanh.approx.f32 t0, t0;\n"
+        "tanh.approx.f32 t1, t1;\n"
+        "mov.b64 c, {t0, t1};\n"
+        "fma.rn.f32x2 c, c, hh, hh;\n"
+        "mov.b64 {%0, %1}, c;\n"
+        "mov.b64 a, {%6, %7};\n"
+        "mov.b64 b, {%10, %11};\n"
+        "add.rn.f32x2 c, a, b;\n"
+        "mul.rn.f32x2 c, c, hh;\n"
+        "mov.b64 {t0, t1}, c;\n"
+        "tanh.approx.f32 t0, t0;\n"
+        "tanh.approx.f32 t1, t1;\n"
+        "mov.b64 c, {t0, t1};\n"
+        "fma.rn.f32x2 c, c, hh, hh;\n"
+        "mov.b64 {%2, %3}, c;\n"
+        "}\n"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3]), "r"(bb.x), "r"(bb.y), "r"(bb.z), "r"(bb.w),
+          "r"(0x3f000000u));
+    pk[2 * i] = pack_bf16x2(__uint_as_float(r0), __uint_as_float(r1));
+    pk[2 * i + 1] = pack_bf16x2(__uint_as_float(r2), __uint_as_float(r3));
+    const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint4 w;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(w4_addr + 16u * (4 * i + e)));
+      asm("{\n"
+          ".reg .b64 y, wa, wb;\n"
+          "mov.b64 y, {%2, %2};\n"
+          "mov.b64 wa, {%3, %4};\n"
+          "mov.b64 wb, {%5, %6};\n"
+          "fma.rn.f32x2 %0, y, wa, %0;\n"
+          "fma.rn.f32x2 %1, y, wb, %1;\n"
+          "}\n"
+          : "+l"(acc01), "+l"(acc23)
+          : "r"(rr[e]), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w));
+    }
+  }
+}
+
 //   dgrad:  round the accumulator to bf16x2, AND with the per-half mask (saved output > 0)
 __device__ __forceinline__ void bwd_relu_packed(const uint32_t (&v)[32], const uint32_t* yw, uint32_t* pk) {
 #pragma unroll
@@ -240,6 +301,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
   auto y_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 4 + i); };   // 2*6+4+12 = 28 barriers max
   const uint32_t tmem_slot = bar_base + 8u * 28;
+  const uint32_t head_smem = bar_base + Cfg::BAR_BYTES;  // EPI_FWD_HEAD with Cfg::HEAD_SMEM: BN x 4 head weights
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // scheduling unit = CTA (CG 1) or CTA pair (CG 2); `rank` = position inside the pair
@@ -360,6 +422,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         const int t = threadIdx.x - 64;    // 0..127
         for (int i = t; i < BN; i += 128)
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + i * 4u), "f"(__ldg(p.bias + n0 + i)) : "memory");
+        if (HEAD && Cfg::HEAD_SMEM) {
+          for (int i = t; i < BN; i += 128) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.head_w4) + n0 + i);
+            st_shared_v4(head_smem + i * 16u, __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w));
+          }
+        }
         epi_bar_sync();
         bias_n0 = n0;
       }
@@ -367,6 +435,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};  // fused head: this row's partial dot products over the tile's columns
+      uint64_t hacc01 = 0ull, hacc23 = 0ull;  // ... the same as fp32 pairs (packed path)
       constexpr bool fused_head = HEAD;
       if (IS_FWD && !tma_out && !fused_head) {
         // fp32-only output = an MLP head: n_valid <= 8 real columns in the first column tile; nothing else of the
@@ -419,6 +488,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           uint32_t v[32];
           tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
           tmem_ld_wait();
+          if (fused_head && Cfg::HEAD_SMEM && p.act == ACT_SIGMOID_FAST) {
+            fwd_sigmoid_fast_head_packed(v, bias_smem + (jj * 64 + h * 32) * 4u, head_smem + (jj * 64 + h * 32) * 16u,
+                                         &packed[16 * h], hacc01, hacc23);
+            continue;
+          }
           if (fused_head) {
             // activation in fp32, then 4 FMAs per column against the head weights (uniform 16-byte loads: every lane
             // of the warp reads the same address, one L1 transaction per load)
@@ -509,7 +583,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         bi = nbi;
         if (bi == 0) bphase ^= 1u;
       }
-      if (fused_head && row < p.M) red_add_v4(p.head_out + (size_t)row * 4, hacc[0], hacc[1], hacc[2], hacc[3]);
+      if (fused_head && row < p.M) {
+        hacc[0] += __uint_as_float((uint32_t)hacc01);
+        hacc[1] += __uint_as_float((uint32_t)(hacc01 >> 32));
+        hacc[2] += __uint_as_float((uint32_t)hacc23);
+        hacc[3] += __uint_as_float((uint32_t)(hacc23 >> 32));
+        red_add_v4(p.head_out + (size_t)row * 4, hacc[0], hacc[1], hacc[2], hacc[3]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -820,6 +900,87 @@ adamw_pack_kernel(const mip360_pack_entry* __restrict__ entries, int n_entries, 
   }
 }
 
+// Backward of a fused (<= 4 wide) head in ONE pass over the saved trunk output Y [M, N] (bf16):
+//   dZ[r, c]  = (sum_h g[r, h] * w4[c, h]) * act'(Y[r, c])      gradient entering the last trunk layer      (dgrad)
+//   dWh[h, c] += sum_r g[r, h] * Y[r, c],   dbh[h] += sum_r g[r, h]                                        (wgrad)
+// replaces head_grad_pack + the 64-column head wgrad and dgrad GEMMs, which read Y twice and move a [M, 64] bf16
+// gradient besides.  HBM-bound: 2N bytes read + 2N written + 16 per row.  A thread owns 8 columns (16-byte loads and
+// stores), a block walks rows in a grid-stride loop with the weight gradient in registers and flushes it once.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const uint16_t* __restrict__ Y, long long M,
+                int N, uint16_t* __restrict__ dZ, float* __restrict__ dWh, int ldw, float* __restrict__ dbh) {
+  const int cols8 = N >> 3;                       // 16-byte column groups per row
+  const int cg = threadIdx.x % cols8;             // this thread's column group (N <= 2048: cols8 <= 256)
+  const int rows_per_pass = blockDim.x / cols8;   // rows a block covers per step
+  const int rsub = threadIdx.x / cols8;
+  const int c0 = cg * 8;
+  float w[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w4) + c0 + i);
+    w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int h = 0; h < 4; ++h) acc[i][h] = 0.f;
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rsub < rows_per_pass) {
+    const long long stride = (long long)gridDim.x * rows_per_pass;
+    constexpr int U = 4;  // rows in flight per thread: all loads of a step are issued before the arithmetic
+    for (long long r0 = (long long)blockIdx.x * rows_per_pass + rsub; r0 < M; r0 += U * stride) {
+      float4 gr[U];
+      uint4 yv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < M) {
+          gr[u] = __ldg(reinterpret_cast<const float4*>(g) + r);
+          yv[u] = __ldg(reinterpret_cast<const uint4*>(Y + r * N + c0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r >= M) break;
+        const uint32_t yw[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+        uint32_t out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float res[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * q + e;
+            const float y = e == 0 ? __uint_as_float(yw[q] << 16) : __uint_as_float(yw[q] & 0xffff0000u);
+            const float dz = gr[u].x * w[i][0] + gr[u].y * w[i][1] + gr[u].z * w[i][2] + gr[u].w * w[i][3];
+            float d = 1.f;
+            if (ACT == ACT_RELU) d = y > 0.f ? 1.f : 0.f;
+            else if (ACT == ACT_SIGMOID) d = y * (1.f - y);
+            res[e] = dz * d;
+            acc[i][0] = fmaf(gr[u].x, y, acc[i][0]);
+            acc[i][1] = fmaf(gr[u].y, y, acc[i][1]);
+            acc[i][2] = fmaf(gr[u].z, y, acc[i][2]);
+            acc[i][3] = fmaf(gr[u].w, y, acc[i][3]);
+          }
+          out[q] = pack_bf16x2(res[0], res[1]);
+        }
+        *reinterpret_cast<uint4*>(dZ + r * N + c0) = make_uint4(out[0], out[1], out[2], out[3]);
+        if (cg == 0) { gsum[0] += gr[u].x; gsum[1] += gr[u].y; gsum[2] += gr[u].z; gsum[3] += gr[u].w; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) atomicAdd(dWh + (long long)h * ldw + c0 + i, acc[i][h]);
+    if (cg == 0 && dbh) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) atomicAdd(dbh + h, gsum[h]);
+    }
+  }
+}
+
 // ---- host side: tensor maps ------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -865,9 +1026,9 @@ static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* 
   using Cfg = LinearCfg<BN, CG, OCC>;
   static bool configured[MAX_DEVICES] = {};  // the attribute is per device (one process may drive several)
   const int dev = current_device();
+  constexpr int SMEM = Cfg::SMEM_BYTES + ((EPI == EPI_FWD_HEAD && Cfg::HEAD_SMEM) ? Cfg::HEAD_BYTES : 0);
   if (!configured[dev]) {
-    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
+    MIP_CUDA(cudaFuncSetAttribute(linear_kernel<BN, EPI, CG, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured[dev] = true;
   }
   CUtensorMap ta, tb, tout, ty;
@@ -882,12 +1043,12 @@ static int launch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t* 
   const int units = sm_count() * OCC / CG;
   const int grid = (tiles < units ? tiles : units) * CG;
   if (CG == 1) {
-    linear_kernel<BN, EPI, CG, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, ty, p);
+    linear_kernel<BN, EPI, CG, OCC><<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, tout, ty, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -986,6 +1147,23 @@ int mip360_linear_fwd_head(const uint16_t* X, const uint16_t* W, const float* bi
   MIP_REQUIRE(act >= 0 && act <= 2, "linear_fwd_head: act=%d", act);
   LinearParams p{bias, out_bf16, nullptr, M, N, K, act == ACT_SIGMOID ? ACT_SIGMOID_FAST : act, 0, 0, head_w4, head_out};
   return dispatch_linear<EPI_FWD_HEAD>(X, W, nullptr, p, (cudaStream_t)stream);
+}
+
+int mip360_head_bwd(const float* g, const float* head_w4, const uint16_t* Y, int M, int N, int act, uint16_t* dZ,
+                    float* dWh, int ldw, float* dbh, mip360_stream_t stream) {
+  MIP_REQUIRE(g && head_w4 && Y && dZ && dWh, "head_bwd: null pointer");
+  MIP_REQUIRE(M > 0 && N >= 64 && N % 64 == 0 && N <= 2048 && ldw >= N, "head_bwd: bad shape M=%d N=%d ldw=%d", M, N, ldw);
+  MIP_REQUIRE(act >= 0 && act <= 2, "head_bwd: act=%d", act);
+  int grid = sm_count() * 4;
+  const int rows_per_pass = 256 / (N / 8);
+  const long long need = ((long long)M + rows_per_pass - 1) / rows_per_pass;
+  if (grid > need) grid = (int)need;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act == ACT_RELU) head_bwd_kernel<ACT_RELU><<<grid, 256, 0, st>>>(g, head_w4, Y, M, N, dZ, dWh, ldw, dbh);
+  else if (act == ACT_SIGMOID) head_bwd_kernel<ACT_SIGMOID><<<grid, 256, 0, st>>>(g, head_w4, Y, M, N, dZ, dWh, ldw, dbh);
+  else head_bwd_kernel<ACT_NONE><<<grid, 256, 0, st>>>(g, head_w4, Y, M, N, dZ, dWh, ldw, dbh);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
 }
 
 int mip360_linear_dgrad(const uint16_t* dY, const uint16_t* Wt, const uint16_t* Yprev, int M, int N, int K, int act,

@@ -62,6 +62,33 @@ int mip360_mlp_fwd_fused_head(const uint16_t* x, int M, const mip360_layer* trun
   return MIP360_OK;
 }
 
+int mip360_mlp_bwd_fused_head(const float* g_out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
+                              const float* head_w4, uint16_t* const* acts, float* const* dW, float* const* db,
+                              uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream) {
+  MIP_REQUIRE(trunk && n_trunk >= 1 && n_trunk <= 32 && head_w4 && acts && dW && db && dz0 && dz1, "mlp_bwd_fused_head: null pointer");
+  if (M <= 0) return MIP360_OK;
+  MIP_REQUIRE(g_out && x, "mlp_bwd_fused_head: null input");
+  const int L = n_trunk;
+  uint16_t* dz = dz0;
+  // head: gradient entering the last trunk layer, head weight and bias gradients, one pass over acts[L-1]
+  int rc = mip360_head_bwd(g_out, head_w4, acts[L - 1], M, trunk[L - 1].n_pad, trunk[L - 1].act, dz, dW[L], trunk[L - 1].n_pad,
+                           db[L], stream);
+  if (rc != MIP360_OK) return rc;
+  for (int l = L - 1; l >= 0; --l) {  // trunk layer l maps (l == 0 ? x : acts[l-1]) -> acts[l]
+    const uint16_t* in = l == 0 ? x : acts[l - 1];
+    rc = mip360_linear_wgrad(dz, in, M, trunk[l].n_pad, trunk[l].k_pad, dW[l], db[l], stream);
+    if (rc != MIP360_OK) return rc;
+    if (l > 0) {
+      MIP_REQUIRE(trunk[l].Wt, "mlp_bwd_fused_head: layer %d has no transposed weights", l);
+      uint16_t* nxt = (dz == dz0) ? dz1 : dz0;
+      rc = mip360_linear_dgrad(dz, trunk[l].Wt, acts[l - 1], M, trunk[l].n_pad, trunk[l].k_pad, trunk[l - 1].act, nxt, stream);
+      if (rc != MIP360_OK) return rc;
+      dz = nxt;
+    }
+  }
+  return MIP360_OK;
+}
+
 int mip360_mlp_bwd(const float* g_out, const float* out, const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk,
                    const mip360_layer* head, int n_valid, uint16_t* const* acts, float* const* dW, float* const* db,
                    uint16_t* dz_head, uint16_t* dz0, uint16_t* dz1, mip360_stream_t stream) {

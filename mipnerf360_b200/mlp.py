@@ -264,9 +264,12 @@ class _MLPFunction(torch.autograd.Function):
         if per_layer:
             # one C call per GEMM: instrumented runs (bench.py's per-kernel table) and the data-parallel trainer,
             # which starts the all-reduce of a layer's gradients as soon as its wgrad has been enqueued
-            dzh = ops.head_grad_pack(g_out, out if head_act == ACT_SIGMOID else None, head_act)
-            ops.linear_wgrad(dzh, saved[L], dW=dWh, db=dbh)
-            dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
+            if ctx.fused:  # head dgrad + wgrad in one pass over the saved trunk output
+                dz = ops.head_bwd(g_out, mlp.head_w4, saved[L], acts[L - 1], dWh, dbh)
+            else:
+                dzh = ops.head_grad_pack(g_out, out if head_act == ACT_SIGMOID else None, head_act)
+                ops.linear_wgrad(dzh, saved[L], dW=dWh, db=dbh)
+                dz = ops.linear_dgrad(dzh, Wht, saved[L], acts[L - 1])
             for l in range(L, 0, -1):  # trunk layer l-1 maps saved[l-1] -> saved[l]
                 ops.linear_wgrad(dz, saved[l - 1], dW=targets[l - 1][0], db=targets[l - 1][1])
                 finish_layer(l - 1)
@@ -282,11 +285,13 @@ class _MLPFunction(torch.autograd.Function):
             dW_ptrs = (ctypes.c_void_p * (L + 1))(*([t[0].data_ptr() for t in targets] + [dWh.data_ptr()]))
             db_ptrs = (ctypes.c_void_p * (L + 1))(*([t[1].data_ptr() for t in targets] + [dbh.data_ptr()]))
             g = ops.f32c(g_out)
-            if ctx.fused:  # the head activation derivative is already in g_out: pack it as is
-                head = _lib.Layer(head.W, head.Wt, head.bias, head.n_pad, head.k_pad, ACT_NONE)
-            _lib.call("mip360_mlp_bwd", g.data_ptr(), out.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
-                      ctypes.byref(head), mlp.n_valid, act_ptrs, dW_ptrs, db_ptrs, dzh.data_ptr(), dz0.data_ptr(),
-                      dz1.data_ptr())
+            if ctx.fused:  # g_out is dL/d(head pre-activation): head dgrad + wgrad in one pass, then the trunk
+                _lib.call("mip360_mlp_bwd_fused_head", g.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
+                          mlp.head_w4.data_ptr(), act_ptrs, dW_ptrs, db_ptrs, dz0.data_ptr(), dz1.data_ptr())
+            else:
+                _lib.call("mip360_mlp_bwd", g.data_ptr(), out.data_ptr(), saved[0].data_ptr(), M, trunk_arr, L,
+                          ctypes.byref(head), mlp.n_valid, act_ptrs, dW_ptrs, db_ptrs, dzh.data_ptr(), dz0.data_ptr(),
+                          dz1.data_ptr())
             for l in range(L - 1, -1, -1):
                 finish_layer(l)
         if direct:  # everything has been added to .grad; autograd has nothing left to accumulate

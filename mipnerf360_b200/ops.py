@@ -585,6 +585,16 @@ def linear_fwd_head(x, Wb, bias, act, head_w4, head_out, want_bf16=True):
     return y
 
 
+def head_bwd(g, head_w4, y, act, dWh, dbh):
+    """Backward of a fused head in one pass over the saved trunk output y [M,N]: returns dZ [M,N] bf16 and accumulates
+    the head's weight / bias gradients into dWh [>=4, N] / dbh [>=4]."""
+    g = f32c(g)
+    M, N = y.shape
+    dz = torch.empty((M, N), device=y.device, dtype=torch.bfloat16)
+    call("mip360_head_bwd", ptr(g), ptr(head_w4), ptr(y), M, N, act, ptr(dz), ptr(dWh), dWh.shape[1], ptr(dbh))
+    return dz
+
+
 def linear_dgrad(dY, Wt, y_prev, act, out=None):
     """dX = (dY Wt^T) .* act'(y_prev): dY bf16 [M,N], Wt bf16 [K,N], y_prev bf16 [M,K]."""
     M, N = dY.shape
