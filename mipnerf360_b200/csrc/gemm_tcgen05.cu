@@ -680,6 +680,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant_
   for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += GEMM_THREADS)
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
   fence_proxy_async_smem();
+  __syncthreads();  // orders the generic-proxy fill above before tcgen05.alloc's write of the TMEM address (once per kernel)
   if (warp == 1) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish<CG>();

@@ -388,7 +388,21 @@ class Trainer:
             if self._eager_calls < self.graph_warmup:
                 self._eager_calls += 1
                 return self._step_eager(rays, pixels)
-            st = self._graphs[key] = self._capture(rays, pixels)
+            saved = (self.sched_step, self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"], dict(self._grads_clean))
+            try:
+                st = self._graphs[key] = self._capture(rays, pixels)
+            except RuntimeError as e:
+                # capture refused (e.g. a tool that serialises streams, an allocator event on uncaptured work): nothing
+                # has run, so restore the host-side counters and keep training eagerly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training iteration failed ({e}); continuing without graphs")
+                self.sched_step, self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"], self._grads_clean = saved
+                self._capture_substep = None
+                self.use_graph = False
+                self.opt.zero_grad()
+                self._grads_clean = {"prop": True, "nerf": True}
+                torch.cuda.synchronize()
+                return self._step_eager(rays, pixels)
         for dst, src in zip(st["rays"], rays):
             dst.copy_(src, non_blocking=True)
         st["pixels"].copy_(pixels, non_blocking=True)
