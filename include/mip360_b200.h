@@ -57,8 +57,9 @@ int mip360_set_option(int key, int value);
 int mip360_level0_t_vals(const float* near, const float* far, const float* s_lin, const float* t_rand,
                          float* t_out, int B, int N, mip360_stream_t stream);
 /* The same with (a) the uniforms of ray.py:106 drawn inside the kernel when use_rng = 1 (Philox4x32-10 keyed by rng_seed;
- * counter = (element b*(N+1)+i, rng_stream, *rng_epoch); u = (word >> 8) * 2^-24; rng_epoch is a device counter — may be
- * NULL = 0 — so that a captured CUDA graph draws new numbers per replay), and (b) with norm_sq != NULL the squared
+ * number i of ray b: counter = (b, (i & 7) | ((i >> 5) << 3), rng_stream, *rng_epoch), output word (i >> 3) & 3,
+ * u = (word >> 8) * 2^-24; rng_epoch is a device counter — may be NULL = 0 — so that a captured CUDA graph draws new
+ * numbers per replay), and (b) with norm_sq != NULL the squared
  * Frobenius norm of the batch's uncontracted means (what mip360_frustum_norm_sq computes from t_out afterwards;
  * parameterization.py:25,75) ACCUMULATED into *norm_sq in the same pass (directions [B,3] required). */
 int mip360_level0_sample(const float* near, const float* far, const float* s_lin, const float* t_rand, int use_rng,
@@ -142,8 +143,8 @@ int mip360_resample_invert(const float* bins, const float* cdf, const float* u, 
 int mip360_resample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
                     int B, int N, float resample_padding, int blur, float* new_t, mip360_stream_t stream);
 /* The same with (a) the jitter of ray.py:33 drawn inside the kernel when use_rng = 1: jitter = u01 * jitter_scale with
- * jitter_scale = 1/M - eps as torch's uniform_(0, 1/M - eps) scales it and u01 from the generator described at
- * mip360_level0_sample (element index b*M + m), and (b) with norm_sq != NULL the squared Frobenius norm of the
+ * jitter_scale = 1/M - eps as torch's uniform_(0, 1/M - eps) scales it and u01 = number m of ray b from the generator
+ * described at mip360_level0_sample, and (b) with norm_sq != NULL the squared Frobenius norm of the
  * uncontracted means of the NEW knots accumulated into *norm_sq (what mip360_frustum_norm_sq computes from new_t). */
 int mip360_resample_sample(const float* t_vals, const float* weights, const float* u_base, const float* jitter,
                            int use_rng, unsigned long long rng_seed, unsigned int rng_stream,

@@ -117,9 +117,11 @@ constexpr float G_EPS = 1e-6f;  // intern/parameterization.py:19
 
 // ---- counter-based random numbers (Philox4x32-10, Salmon et al. 2011) ------------------------------------------
 // The randomized draws of the reference (torch.rand of ray.py:106, uniform_ of ray.py:33) are generated inside the
-// kernels that consume them instead of being written to HBM and read back.  One uniform per (stream, element):
-//   counter = (element low, element high, stream id, epoch), key = 64-bit seed,
-//   u = (first output word >> 8) * 2^-24  in [0, 1).
+// kernels that consume them instead of being written to HBM and read back.  Uniform number m of ray r in a draw:
+//   counter = (r, block(m), stream id, epoch), key = 64-bit seed, u = (output word word(m) >> 8) * 2^-24 in [0, 1)
+//   block(m) = (m & 7) | ((m >> 5) << 3),  word(m) = (m >> 3) & 3
+// i.e. one Philox call yields the numbers m, m + 8, m + 16, m + 24 of a ray: exactly the samples one lane of an 8-lane ray
+// group owns (ray_group.cuh), so a lane needs one call per four samples instead of one per sample.
 // `stream id` distinguishes the call sites of one iteration (host counter), `epoch` is read from device memory so that
 // a captured CUDA graph draws fresh numbers on every replay.  (The test suite carries a NumPy restatement, pinned to the
 // published Random123 known-answer vectors, that reproduces these uniforms bit for bit.)
@@ -129,9 +131,8 @@ struct RngArgs {
   unsigned int stream_id;
   int enabled;
 };
-__device__ __forceinline__ uint32_t philox_first_word(unsigned long long seed, unsigned long long element,
-                                                      uint32_t stream_id, uint32_t epoch) {
-  uint32_t c0 = (uint32_t)element, c1 = (uint32_t)(element >> 32), c2 = stream_id, c3 = epoch;
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, unsigned long long seed,
+                                              uint32_t (&out)[4]) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -142,13 +143,25 @@ __device__ __forceinline__ uint32_t philox_first_word(unsigned long long seed, u
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  return c0;
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-__device__ __forceinline__ float rng_uniform(const RngArgs& r, uint32_t epoch, unsigned long long element) {
-  return (float)(philox_first_word(r.seed, element, r.stream_id, epoch) >> 8) * 5.9604644775390625e-08f;
-}
+__device__ __forceinline__ float rng_word_to_uniform(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-08f; }
 __device__ __forceinline__ uint32_t rng_epoch(const RngArgs& r) {
   return r.epoch ? (uint32_t)(*r.epoch) : 0u;
+}
+// the four uniforms m0, m0 + 8, m0 + 16, m0 + 24 (m0 = (block & 7) + 32 * (block >> 3)) of ray `ray`
+__device__ __forceinline__ void rng_uniform4(const RngArgs& r, uint32_t epoch, uint32_t ray, uint32_t block, float (&u)[4]) {
+  uint32_t w[4];
+  philox4x32_10(ray, block, r.stream_id, epoch, r.seed, w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = rng_word_to_uniform(w[i]);
+}
+// uniform number m of ray `ray` (one call per number: the generic kernels)
+__device__ __forceinline__ float rng_uniform(const RngArgs& r, uint32_t epoch, uint32_t ray, uint32_t m) {
+  uint32_t w[4];
+  philox4x32_10(ray, (m & 7u) | ((m >> 5) << 3), r.stream_id, epoch, r.seed, w);
+  const uint32_t sel = (m >> 3) & 3u;
+  return rng_word_to_uniform(sel == 0 ? w[0] : sel == 1 ? w[1] : sel == 2 ? w[2] : w[3]);
 }
 
 }  // namespace mip360

@@ -52,9 +52,12 @@ __device__ __forceinline__ void ray_weights(const CompositeSmem& s, int N, int C
 }
 
 // head_mode 2: raw holds the heads' pre-activation sums without bias -> Sigmoid(raw + bias) (model.py:150-158)
+// The head activation as the GEMM epilogue evaluates it for an unfused head (1 / (1 + e^-z) with the fast exp and
+// reciprocal: ~2 ulp, and the same values whichever side applies the Sigmoid)
+__device__ __forceinline__ float head_sigmoid_one(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 __device__ __forceinline__ float4 head_sigmoid(float4 v, const float* __restrict__ head_bias) {
-  return make_float4(sigmoid_f(v.x + __ldg(head_bias)), sigmoid_f(v.y + __ldg(head_bias + 1)),
-                     sigmoid_f(v.z + __ldg(head_bias + 2)), sigmoid_f(v.w + __ldg(head_bias + 3)));
+  return make_float4(head_sigmoid_one(v.x + __ldg(head_bias)), head_sigmoid_one(v.y + __ldg(head_bias + 1)),
+                     head_sigmoid_one(v.z + __ldg(head_bias + 2)), head_sigmoid_one(v.w + __ldg(head_bias + 3)));
 }
 // ... and its derivative y (1 - y) folded into the gradient of the four head outputs; y0 is kept, the colours are
 // recovered from the padded values c = y * scale - pad

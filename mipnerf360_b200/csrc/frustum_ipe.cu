@@ -528,7 +528,7 @@ level0_t_kernel(const float* __restrict__ near, const float* __restrict__ far, c
       if (!randomized) return tk;
       const float upper = (k < N) ? 0.5f * (t_next + tk) : tk;
       const float lower = (k > 0) ? 0.5f * (tk + t_prev) : tk;
-      const float u = t_rand ? t_rand[(long long)b * K + k] : rng_uniform(rng, epoch, (unsigned long long)b * K + k);
+      const float u = t_rand ? t_rand[(long long)b * K + k] : rng_uniform(rng, epoch, (uint32_t)b, (uint32_t)k);
       return lower + (upper - lower) * u;
     };
     const float t_im1 = i > 0 ? tv(i - 1) : 0.f, t_i = tv(i), t_ip1 = i < N ? tv(i + 1) : 0.f;
@@ -553,6 +553,91 @@ level0_t_kernel(const float* __restrict__ near, const float* __restrict__ far, c
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int w = 0; w < 8; ++w) s += sm[w];
+      atomicAdd(norm_sq, s);
+    }
+  }
+}
+
+// The same for N in {32, 64, 128} with 8 lanes per ray (ray_group.cuh): lane gl owns knots gl + 8c, so the group writes 8
+// consecutive floats per step, the deterministic knots of the neighbours i - 1 / i + 1 and the jittered knot i + 1 come from
+// the adjacent lanes by shuffle instead of being recomputed, and the lane's E + 1 uniforms cost E / 4 + 1 Philox calls.
+template <int E>
+__global__ void __launch_bounds__(RG_THREADS)
+level0_t_rg_kernel(const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ s_lin,
+                   const float* __restrict__ t_rand, RngArgs rng, const float* __restrict__ directions,
+                   double* __restrict__ norm_sq, float* __restrict__ t_out, int B) {
+  constexpr int N = E * RG_LANES, K = N + 1, S = E + 1;
+  const int gl = threadIdx.x & 7;
+  const bool randomized = t_rand != nullptr || rng.enabled;
+  const uint32_t epoch = rng.enabled ? rng_epoch(rng) : 0u;
+  float sl[S];
+#pragma unroll
+  for (int c = 0; c < S; ++c) sl[c] = __ldg(s_lin + ((c < E) ? gl + RG_LANES * c : N));
+  double acc = 0.0;
+  for (long long base = (long long)blockIdx.x * RG_RAYS_PER_BLOCK; base < B; base += (long long)gridDim.x * RG_RAYS_PER_BLOCK) {
+    const long long ray_raw = base + (threadIdx.x >> 3);
+    const bool active = ray_raw < B;
+    const long long ray = active ? ray_raw : B - 1;
+    const float gf = g_disp(__ldg(far + ray)), gn = g_disp(__ldg(near + ray));
+    float u[S];
+    if (t_rand) {
+#pragma unroll
+      for (int c = 0; c < S; ++c) u[c] = __ldg(t_rand + ray * K + ((c < E) ? gl + RG_LANES * c : N));
+    } else if (rng.enabled) {
+      rg_draw<E>(rng, epoch, (uint32_t)ray, gl, u);
+    }
+    float tv[S];  // deterministic knots: slot c = knot gl + 8c, slot E = knot N (every lane computes it; lane 0 uses it)
+#pragma unroll
+    for (int c = 0; c < S; ++c) tv[c] = g_disp(sl[c] * gf + (1.f - sl[c]) * gn);
+    float t[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) {
+      float v = tv[c];
+      if (randomized) {
+        // knot i - 1: the previous lane's knot of this slot, or lane 7's knot of the previous slot; knot i + 1: the next
+        // lane's, or lane 0's next slot (slot E = knot N for c = E - 1)
+        const float up = __shfl_up_sync(FULL_MASK, tv[c], 1, RG_LANES);
+        const float l7 = __shfl_sync(FULL_MASK, tv[c > 0 ? c - 1 : 0], RG_LANES - 1, RG_LANES);
+        const float dn = __shfl_down_sync(FULL_MASK, tv[c], 1, RG_LANES);
+        const float l0 = __shfl_sync(FULL_MASK, tv[c < E ? c + 1 : E], 0, RG_LANES);
+        const int k = (c < E) ? gl + RG_LANES * c : N;
+        const float t_prev = gl == 0 ? l7 : up, t_next = gl == RG_LANES - 1 ? l0 : dn;
+        // slot E (knot N, valid in lane 0): its predecessor is knot N - 1 = lane 7's slot E - 1
+        const float prev = (c == E) ? __shfl_sync(FULL_MASK, tv[E - 1], RG_LANES - 1, RG_LANES) : t_prev;
+        const float upper = (k < N) ? 0.5f * (t_next + v) : v;
+        const float lower = (k > 0) ? 0.5f * (v + prev) : v;
+        v = lower + (upper - lower) * u[c];
+      }
+      t[c] = v;
+    }
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < E; ++c) t_out[ray * K + gl + RG_LANES * c] = t[c];
+      if (gl == 0) t_out[ray * K + N] = t[E];
+    }
+    if (norm_sq) {
+      const float d0 = __ldg(directions + ray * 3), d1 = __ldg(directions + ray * 3 + 1), d2 = __ldg(directions + ray * 3 + 2);
+#pragma unroll
+      for (int c = 0; c < E; ++c) {
+        const float dn = __shfl_down_sync(FULL_MASK, t[c], 1, RG_LANES);
+        const float l0 = __shfl_sync(FULL_MASK, t[c + 1], 0, RG_LANES);
+        const float t0 = t[c], t1 = gl == RG_LANES - 1 ? l0 : dn;
+        const float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
+        const float hw2 = hw * hw;
+        const float t_mean = mu + (2.f * mu * hw2) / (3.f * (mu * mu) + hw2);
+        const float m0 = d0 * t_mean, m1 = d1 * t_mean, m2 = d2 * t_mean;
+        if (active) acc += (double)(m0 * m0 + m1 * m1 + m2 * m2);
+      }
+    }
+  }
+  if (norm_sq) {
+    acc = warp_sum(acc);
+    __shared__ double sm[RG_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < RG_THREADS / 32; ++i) s += sm[i];
       atomicAdd(norm_sq, s);
     }
   }
@@ -586,8 +671,15 @@ int mip360_level0_sample(const float* near, const float* far, const float* s_lin
   if (B == 0) return MIP360_OK;
   const long long total = (long long)B * (N + 1);
   RngArgs rng{rng_seed, rng_epoch, rng_stream, use_rng ? 1 : 0};
-  level0_t_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, s_lin, t_rand, rng, directions,
-                                                                          norm_sq, t_out, B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rg_supported_host(N) && N == 32)
+    level0_t_rg_kernel<4><<<rg_grid(B), RG_THREADS, 0, st>>>(near, far, s_lin, t_rand, rng, directions, norm_sq, t_out, B);
+  else if (rg_supported_host(N) && N == 64)
+    level0_t_rg_kernel<8><<<rg_grid(B), RG_THREADS, 0, st>>>(near, far, s_lin, t_rand, rng, directions, norm_sq, t_out, B);
+  else if (rg_supported_host(N) && N == 128)
+    level0_t_rg_kernel<16><<<rg_grid(B), RG_THREADS, 0, st>>>(near, far, s_lin, t_rand, rng, directions, norm_sq, t_out, B);
+  else
+    level0_t_kernel<<<blocks_for(total, 256), 256, 0, st>>>(near, far, s_lin, t_rand, rng, directions, norm_sq, t_out, B, N);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
 }

@@ -232,8 +232,12 @@ interlevel_kernel(const float* __restrict__ w_hat, const float* __restrict__ b_p
   double acc = 0.0;
   float g_scale = 0.f;
   if (BWD) g_scale = *g_loss_ptr / batch_div;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e % N);
+  // column index carried along instead of a 64-bit modulo per element: i = e mod N advances by (stride mod N) per step
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int step = (int)(stride % N);
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int i = (int)(e % N);
+  for (; e < total; e += stride, i = (i + step >= N ? i + step - N : i + step)) {
     const float bnd = bound_mode == 0 ? (float)bound_total[i] : b_per_ray[e];
     const float w = w_hat[e];
     const float r = fmaxf(bnd - w, 0.f);

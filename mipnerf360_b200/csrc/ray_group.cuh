@@ -66,6 +66,24 @@ __device__ __forceinline__ void rg_load_knots(const float* __restrict__ row, int
   for (int i = 0; i <= E; ++i) t[i] = __ldg(row + j0 + i);
 }
 
+// The lane's E + 1 uniforms of a draw (common.cuh): slot c < E is number gl + 8c of the ray, slot E is number N = 8E (used
+// by lane 0 only).  E / 4 Philox calls for the first E slots (at least one), one more for slot E.
+template <int E>
+__device__ __forceinline__ void rg_draw(const RngArgs& rng, uint32_t epoch, uint32_t ray, int gl, float (&u)[E + 1]) {
+#pragma unroll
+  for (int j = 0; j < (E + 3) / 4; ++j) {
+    float q[4];
+    rng_uniform4(rng, epoch, ray, (uint32_t)(gl + 8 * j), q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * j + i < E) u[4 * j + i] = q[i];
+  }
+  // number N = 8E: lane 0 of block 8 * (E / 4), word E & 3 (the whole warp executes the call, lane 0 uses it)
+  float q[4];
+  rng_uniform4(rng, epoch, ray, (uint32_t)(8 * (E / 4)), q);
+  u[E] = (E & 3) == 0 ? q[0] : q[E & 3];
+}
+
 static inline int rg_grid(int B) {
   long long b = ((long long)B + RG_RAYS_PER_BLOCK - 1) / RG_RAYS_PER_BLOCK;
   const long long cap = (long long)sm_count() * 32;

@@ -155,7 +155,7 @@ resample_kernel(const float* __restrict__ t_vals, const float* __restrict__ weig
       if (jitter || rng.enabled) {
         // ray.py:33: uniform_(0, 1/M - eps) — a given draw, or the in-kernel generator scaled the way torch scales it
         const float jit = jitter ? jitter[(long long)b * K + m]
-                                 : rng_uniform(rng, epoch, (unsigned long long)b * K + m) * jitter_scale;
+                                 : rng_uniform(rng, epoch, (uint32_t)b, (uint32_t)m) * jitter_scale;
         u = (u + u) + jit;  // the doubled stratum offset is the reference's (App. A5)
         u = fminf(u, one_m_eps);
       }
@@ -277,9 +277,9 @@ resample_rg_kernel(const float* __restrict__ t_vals, const float* __restrict__ w
       for (int c = 0; c <= E; ++c) jit[c] = __ldg(jitter + ray * K + ((c < E) ? gl + RG_LANES * c : N));
     } else if (rng.enabled) {
       // ray.py:33 drawn here instead of being read: uniform_(0, 1/M - eps) = u01 * (1/M - eps)
+      rg_draw<E>(rng, epoch, (uint32_t)ray, gl, jit);
 #pragma unroll
-      for (int c = 0; c <= E; ++c)
-        jit[c] = rng_uniform(rng, epoch, (unsigned long long)ray * K + ((c < E) ? gl + RG_LANES * c : N)) * jitter_scale;
+      for (int c = 0; c <= E; ++c) jit[c] = jit[c] * jitter_scale;
     }
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     if (norm_sq) { d0 = __ldg(directions + ray * 3); d1 = __ldg(directions + ray * 3 + 1); d2 = __ldg(directions + ray * 3 + 2); }

@@ -5,8 +5,9 @@ Tensor.uniform_ (intern/ray.py:106 and :33); the CUDA path generates them inside
 (mipnerf360_b200/csrc/common.cuh: philox_first_word, rng_uniform).  This file reproduces those uniforms bit for bit so
 that the randomized kernels can be checked against the oracle fed the same numbers.
 
-Convention: counter = (element & 0xffffffff, element >> 32, stream_id, epoch), key = (seed & 0xffffffff, seed >> 32),
-u = (first output word >> 8) * 2**-24.  Pinned by the known-answer vectors of the Random123 distribution
+Convention: number m of ray r in a draw: counter = (r, (m & 7) | ((m >> 5) << 3), stream_id, epoch),
+key = (seed & 0xffffffff, seed >> 32), u = (output word (m >> 3) & 3 >> 8) * 2**-24 — one Philox call yields the numbers
+m, m + 8, m + 16, m + 24 of a ray.  Pinned by the known-answer vectors of the Random123 distribution
 (tests/test_oracle_properties_cpu.py)."""
 import numpy as np
 
@@ -29,9 +30,11 @@ def philox4x32_10(counter, key):
 
 
 def uniform(seed, stream_id, epoch, shape):
-    """The float32 uniforms in [0, 1) the kernels draw for a tensor of `shape` (element index = flat C-order index)."""
-    n = int(np.prod(shape))
-    e = np.arange(n, dtype=np.uint64)
-    w = philox4x32_10((e & MASK, e >> np.uint64(32), np.uint64(stream_id), np.uint64(epoch)),
-                      (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
-    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).reshape(shape)
+    """The float32 uniforms in [0, 1) the kernels draw for a [rays, numbers-per-ray] tensor."""
+    B, K = shape
+    r, m = np.meshgrid(np.arange(B, dtype=np.uint64), np.arange(K, dtype=np.uint64), indexing="ij")
+    block = (m & np.uint64(7)) | ((m >> np.uint64(5)) << np.uint64(3))
+    words = philox4x32_10((r, block, np.uint64(stream_id), np.uint64(epoch)), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    sel = ((m >> np.uint64(3)) & np.uint64(3)).astype(np.int64)
+    w = np.choose(sel, words)
+    return (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)

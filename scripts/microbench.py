@@ -54,12 +54,15 @@ def gen_rays(B):
                 torch.full((B, 1), 0.1, device=DEV), torch.full((B, 1), 10.0, device=DEV))
 
 
+SWEEP_B = (1 << 20, 1 << 22, 1 << 24, 1 << 26)
+
+
 def micro(out_path):
     pk = peak_hbm()
     rows = []
     free = torch.cuda.mem_get_info()[0]
     for N in (32, 64, 128):
-        for B in (1 << 20, 1 << 22, 1 << 24, 1 << 26):
+        for B in SWEEP_B:
             knots = B * (N + 1) * 4
             if 8 * knots > 0.8 * free:
                 continue
@@ -77,6 +80,18 @@ def micro(out_path):
             # K4 resample (blur + pdf + cdf + inverse cdf), randomized with supplied jitter
             ms = timeit(lambda: ops.resample(t, w, True, 0.01, jitter=jit))
             rec("resample", ms, 4 * (3 * N + 2) + 4 * (N + 1))
+            # the model path: jitter drawn inside the kernel (Philox) and the contraction norm of the new knots accumulated
+            dirs0 = torch.randn(B, 3, device=DEV)
+            nsq = torch.zeros(1, device=DEV, dtype=torch.float64)
+            ms = timeit(lambda: ops.resample(t, w, True, 0.01, directions=dirs0, norm_sq=nsq))
+            rec("resample_rng_norm", ms, 4 * (3 * N + 2) + 12)
+            # K0 level-0 sampling with in-kernel draw + norm
+            near, far = torch.full((B, 1), 0.1, device=DEV), torch.full((B, 1), 10.0, device=DEV)
+            ms = timeit(lambda: ops.level0_t_vals(near, far, N, True, directions=dirs0, norm_sq=nsq))
+            rec("level0_rng_norm", ms, 4 * (N + 1) + 8 + 12)
+            ms = timeit(lambda: ops.level0_t_vals(near, far, N, False))
+            rec("level0_deterministic", ms, 4 * (N + 1) + 8)
+            del dirs0, near, far
             # K5 distortion forward / backward
             s = t / t[:, -1:]
             ms = timeit(lambda: ops.distortion_per_ray(s, w))
@@ -98,13 +113,33 @@ def micro(out_path):
                 g_rgb, g_w = torch.rand(B, 3, device=DEV), torch.rand(B, N, device=DEV)
                 g_raw = torch.empty_like(raw)
                 ms = timeit(lambda: ops.call("mip360_composite_bwd", raw.data_ptr(), None, t.data_ptr(), dirs.data_ptr(), B, N,
-                                             1, -1.0, 0.001, 0, g_rgb.data_ptr(), None, g_w.data_ptr(), None, None,
-                                             g_raw.data_ptr()))
+                                             1, -1.0, 0.001, 0, g_rgb.data_ptr(), None, None, g_w.data_ptr(), None, None,
+                                             g_raw.data_ptr(), None))
                 rec("composite_bwd_heads", ms, 16 * N + 4 * (N + 1) + 12 + 12 + 4 * N + 16 * N)
+                # the model path: heads' bias + Sigmoid applied here (fused-head MLP) and t_to_s in the same launch
+                hb = torch.zeros(64, device=DEV)
+                nr, fr = torch.full((B, 1), 0.1, device=DEV), torch.full((B, 1), 10.0, device=DEV)
+                ms = timeit(lambda: ops.composite_heads(raw, t, dirs, -1.0, 0.001, False, near=nr, far=fr, head_bias=hb))
+                rec("composite_fwd_logits_t_to_s", ms, 16 * N + 4 * (N + 1) + 12 + 8 + 20 + 4 * N + 8 * (N + 1))
+                ms = timeit(lambda: ops.call("mip360_composite_bwd", raw.data_ptr(), None, t.data_ptr(), dirs.data_ptr(), B, N,
+                                             2, -1.0, 0.001, 0, g_rgb.data_ptr(), None, None, g_w.data_ptr(), None, None,
+                                             g_raw.data_ptr(), hb.data_ptr()))
+                rec("composite_bwd_logits", ms, 16 * N + 4 * (N + 1) + 12 + 12 + 4 * N + 16 * N)
+                del hb, nr, fr
                 del raw, g_rgb, g_w, g_raw
             t2 = (torch.rand(B, N + 1, device=DEV) * 0.3).cumsum_(-1).add_(0.1)
             ms = timeit(lambda: ops.bounds_per_ray(t, w, t2))
             rec("bounds_per_ray", ms, 4 * (3 * N + 2) + 4 * N)
+            ms = timeit(lambda: ops.bounds_batch_total(t, w, t2))
+            rec("bounds_batch_total", ms, 4 * (3 * N + 2))
+            tot = torch.rand(N, device=DEV, dtype=torch.float64)
+            ms = timeit(lambda: ops.interlevel_loss(w, bound_total=tot))
+            rec("interlevel_fwd", ms, 4 * N)
+            gw2 = torch.empty_like(w)
+            ms = timeit(lambda: ops.call("mip360_interlevel_bwd", w.data_ptr(), None, tot.data_ptr(), B, N, 0, float(B),
+                                         g1.data_ptr(), gw2.data_ptr()))
+            rec("interlevel_bwd", ms, 8 * N)
+            del gw2, tot
             del t2, jit
             # K1 fused cast -> Gaussian -> contract -> IPE, bf16 [N,64] rows (the model path variant)
             if B * N * 128 < 0.45 * free:
@@ -252,7 +287,10 @@ if __name__ == "__main__":
     ap.add_argument("mode", choices=["micro", "render", "visualize"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--chunks", type=int, default=65536)
+    ap.add_argument("--rays", default=None, help="micro: comma-separated ray counts instead of the 1M..64M sweep")
     a = ap.parse_args()
+    if a.rays:
+        SWEEP_B = tuple(int(x) for x in a.rays.split(","))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out = a.out or os.path.join(ROOT, "gpurun_out", f"{a.mode}.json")
     t0 = time.time()
