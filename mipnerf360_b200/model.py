@@ -221,19 +221,10 @@ class mipNeRF360(nn.Module):
     def render_image(self, rays, height, width, chunks=4096):
         """model.py:254-274: chunked inference.  Results stay on the device until the end (one D2H copy per
         output instead of three per chunk plus a print)."""
-        length = rays[0].shape[0]
-        rgbs, dists, accs = [], [], []
-        with torch.no_grad():
-            for i in range(0, length, chunks):
-                chunk_rays = namedtuple_map(lambda r: r[i:i + chunks].to(self.device, non_blocking=True), rays)
-                rgb, distance, acc = self(chunk_rays)
-                rgbs.append(rgb)
-                dists.append(distance)
-                accs.append(acc)
-        rgbs = ops.to8b(torch.cat(rgbs, dim=0).reshape(height, width, 3)).cpu().numpy()  # 3 B/pixel over PCIe
-        dists = torch.cat(dists, dim=0).reshape(height, width).cpu().numpy()
-        accs = torch.cat(accs, dim=0).reshape(height, width).cpu().numpy()
-        return rgbs, dists, accs
+        from mipnerf360_b200.render import render_rays  # chunk loop (one CUDA-graph replay per full chunk)
+        rgb, dists, accs = render_rays(self, rays, chunks)
+        rgbs = ops.to8b(rgb.reshape(height, width, 3)).cpu().numpy()  # 3 B/pixel over PCIe
+        return rgbs, dists.reshape(height, width).cpu().numpy(), accs.reshape(height, width).cpu().numpy()
 
     def train(self, mode=True):
         """model.py:276-279."""

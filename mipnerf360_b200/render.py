@@ -33,17 +33,73 @@ def _world(group=None):
     return 1, 0
 
 
-def render_rays(model, rays, chunks):
+class ChunkForward:
+    """model(chunk) for a fixed chunk size as ONE CUDA-graph replay: the ~35 kernel launches of an inference forward
+    and the Python between them collapse into one launch, which is what a render loop with small chunks (the reference's
+    defaults are 4096, model.py:254, and 128, config.py:49) spends its time on.  Inputs are copied into static buffers;
+    randomized sampling keeps working because the in-kernel generator reads its replay counter from device memory.
+    Chunks of another size (the ragged last one) run eagerly.  Falls back to eager execution if capture is refused."""
+
+    def __init__(self, model, chunk_rays):
+        self.model, self.n = model, int(chunk_rays)
+        self.graph = None
+        self.failed = False
+        self.warm = False
+
+    def _capture(self, chunk):
+        from mipnerf360_b200.intern.ray import Rays
+        self.static_in = Rays(*[r.detach().clone() for r in chunk])
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g, capture_error_mode="thread_local"):
+            ops.rng_advance(self.static_in.origins.device)
+            self.static_out = self.model(self.static_in)
+        self.graph = g
+
+    def __call__(self, chunk):
+        if chunk[0].shape[0] != self.n or self.failed or not chunk[0].is_cuda:
+            with torch.no_grad():
+                return self.model(chunk)
+        if not self.warm:
+            # the first full chunk runs eagerly (and counts): lazy kernel attributes, operand refresh, allocator pools
+            self.warm = True
+            with torch.no_grad():
+                return self.model(chunk)
+        if self.graph is None:
+            try:
+                self._capture(chunk)
+            except RuntimeError:
+                self.failed = True
+                torch.cuda.synchronize()
+                with torch.no_grad():
+                    return self.model(chunk)
+        for dst, src in zip(self.static_in, chunk):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
+def _chunk_runner(model, n, chunks, graph):
+    """A callable chunk -> (rgb, dist, acc): graph replays when the loop is long enough to repay the capture."""
+    if graph and n >= 4 * chunks and torch.cuda.is_available():
+        return ChunkForward(model, chunks)
+
+    def eager(chunk):
+        with torch.no_grad():
+            return model(chunk)
+    return eager
+
+
+def render_rays(model, rays, chunks, graph=True):
     """Chunk loop of model.render_image on device-resident or host rays -> (rgb [n,3], dist [n], acc [n]) on device."""
     n = rays[0].shape[0]
     dev = next(model.parameters()).device
     rgb = torch.empty((n, 3), device=dev)
     d = torch.empty((n,), device=dev)
     a = torch.empty((n,), device=dev)
-    with torch.no_grad():
-        for i in range(0, n, chunks):
-            chunk = namedtuple_map(lambda r: r[i:i + chunks].to(dev, non_blocking=True), rays)
-            rgb[i:i + chunks], d[i:i + chunks], a[i:i + chunks] = model(chunk)
+    run = _chunk_runner(model, n, chunks, graph)
+    for i in range(0, n, chunks):
+        chunk = namedtuple_map(lambda r: r[i:i + chunks].to(dev, non_blocking=True), rays)
+        rgb[i:i + chunks], d[i:i + chunks], a[i:i + chunks] = run(chunk)
     return rgb, d, a
 
 
@@ -62,14 +118,14 @@ def gather_slabs(local, n, world, group=None, per=None):
     return out[:n]
 
 
-def render_image_distributed(model, rays, height, width, chunks=4096, group=None):
+def render_image_distributed(model, rays, height, width, chunks=4096, group=None, graph=True):
     """Every rank passes the full ray set (host tensors are fine) and receives the full image:
     (rgb [h,w,3] float, dist [h,w], acc [h,w]) on the device.  world_size 1 degenerates to render_rays."""
     world, rank = _world(group)
     n = rays[0].shape[0]
     lo, hi = shard_bounds(n, rank, world, align=chunks)
     mine = namedtuple_map(lambda r: r[lo:hi], rays)
-    rgb, d, a = render_rays(model, mine, chunks)  # chunks are independent: model() issues no collective
+    rgb, d, a = render_rays(model, mine, chunks, graph)  # chunks are independent: model() issues no collective
     if world > 1:
         per = shard_bounds(n, 0, world, align=chunks)[1]
         packed = gather_slabs(torch.cat([rgb, d[:, None], a[:, None]], dim=1), n, world, group, per=per)
@@ -78,7 +134,7 @@ def render_image_distributed(model, rays, height, width, chunks=4096, group=None
 
 
 def render_frame(model, cam_to_world, height, width, focal, near, far, ndc=False, chunks=4096, group=None,
-                 to_host=True):
+                 to_host=True, graph=True):
     """One camera -> (uint8 [h,w,3], dist [h,w], acc [h,w]) like model.render_image (model.py:254-274), with the
     rays generated on the device chunk by chunk.  Under torch.distributed every rank renders its slab and
     receives the whole frame.  to_host: return NumPy arrays (one D2H copy per output), else device tensors."""
@@ -92,11 +148,12 @@ def render_frame(model, cam_to_world, height, width, focal, near, far, ndc=False
     d = torch.empty((m,), device=dev)
     a = torch.empty((m,), device=dev)
     torch.cuda.nvtx.range_push("mip360/render_frame")
+    run = _chunk_runner(model, m, chunks, graph)
     with torch.no_grad():
         for i in range(0, m, chunks):
             c = min(chunks, m - i)
             chunk = ops.generate_rays(c2w, height, width, focal, near, far, ndc=ndc, ray_begin=lo + i, ray_count=c)
-            rgb[i:i + c], d[i:i + c], a[i:i + c] = model(chunk)
+            rgb[i:i + c], d[i:i + c], a[i:i + c] = run(chunk)
     torch.cuda.nvtx.range_pop()
     rgb8 = ops.to8b(rgb)  # the picture leaves the device (and crosses NVLink) as 3 B/pixel
     if world > 1:

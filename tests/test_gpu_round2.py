@@ -698,3 +698,36 @@ def test_fused_head_equals_separate_head_gemm():
             _lib.PROFILE = None
         assert "mip360_linear_fwd_head" in names
         close(prof_rgb, a["rgb"], rtol=1e-6, atol=1e-6)
+
+
+def test_graphed_render_chunks_equal_eager_chunks(ops):
+    """render loops replay one CUDA graph per full chunk: same pictures as the eager chunk loop, ragged last chunk and
+    frames too short for a capture included; weights changed between two renders are picked up."""
+    from mipnerf360_b200.model import mipNeRF360
+    from mipnerf360_b200.render import render_frame, render_rays
+    from mipnerf360_b200.synthetic import garden_case
+    dev = torch.device(DEV)
+    torch.manual_seed(3)
+    m = mipNeRF360(randomized=False, num_samples=32, hidden_proposal=64, hidden_nerf=128, device=dev)
+    case = garden_case(30, 37)  # 1110 rays
+    args = (case["c2w"], 30, 37, case["focal"], case["near"], case["far"], case["ndc"])
+    for chunks in (100, 256, 2000):
+        a = render_frame(m, *args, chunks=chunks, graph=True)
+        b = render_frame(m, *args, chunks=chunks, graph=False)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), chunks
+    rays = ops.generate_rays(case["c2w"].to(dev), 30, 37, case["focal"], case["near"], case["far"])
+    before = render_rays(m, rays, 100)[0].clone()
+    with torch.no_grad():
+        for p in m.nerf_net.final_color.parameters():
+            p.add_(0.5)
+    after_g, after_e = render_rays(m, rays, 100, graph=True)[0], render_rays(m, rays, 100, graph=False)[0]
+    assert torch.equal(after_g, after_e) and not torch.equal(after_g, before)
+    # randomized sampling under replay: fresh draws every chunk (and every frame)
+    for net in (m, m.prop_net, m.nerf_net):
+        net.randomized = True
+    r1, r2 = render_rays(m, rays, 100)[0], render_rays(m, rays, 100)[0]
+    assert torch.isfinite(r1).all() and not torch.equal(r1, r2)
+    same_rays = O.Rays(*[x[:100].repeat(5, 1) for x in rays])  # five identical chunks must not render identically
+    rr = render_rays(m, same_rays, 100)[0].view(5, 100, 3)
+    assert not torch.equal(rr[2], rr[3]) and not torch.equal(rr[3], rr[4])
