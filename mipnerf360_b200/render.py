@@ -78,9 +78,13 @@ class ChunkForward:
         return self.static_out
 
 
+GRAPH_MAX_CHUNK = 16384  # rays: above this a chunk is GPU-bound (>= 15 ms of GEMMs) and a private graph pool only costs memory
+
+
 def _chunk_runner(model, n, chunks, graph):
-    """A callable chunk -> (rgb, dist, acc): graph replays when the loop is long enough to repay the capture."""
-    if graph and n >= 4 * chunks and torch.cuda.is_available():
+    """A callable chunk -> (rgb, dist, acc): graph replays when the loop is long enough to repay the capture and the
+    chunks are small enough to be launch-bound."""
+    if graph and n >= 4 * chunks and chunks <= GRAPH_MAX_CHUNK and torch.cuda.is_available():
         return ChunkForward(model, chunks)
 
     def eager(chunk):
