@@ -175,10 +175,10 @@ def kernel_work(name, a):
     if name == "mip360_cast_ipe_x":       # t_stride, vd_dim, B, N, mode, flags, x_cols : bf16 [N, x_cols] output variant
         B, N, cols = a[2], a[3], a[6]
         return "hbm", B * (48.0 + 4 * (N + 1) + 2 * cols * N)
-    if name == "mip360_level0_sample":    # use_rng, seed, stream, B, N : writes the knots (reads 8 B/ray)
+    if name == "mip360_level0_sample":    # (use_rng, stream,) B, N : writes the knots (reads 20 B/ray)
         B, N = a[-2], a[-1]
         return "hbm", B * (4.0 * (N + 1) + 8 + 12)
-    if name == "mip360_resample_sample":  # use_rng, seed, stream, B, N, blur : bins + weights in, knots out
+    if name == "mip360_resample_sample":  # (use_rng, stream,) B, N, blur : bins + weights in, knots out
         B, N = a[-3], a[-2]
         return "hbm", B * (4.0 * (3 * N + 2) + 12)
     if name == "mip360_composite_fwd_s":  # B, N, head_mode, white : + s_vals and t_shift rows
@@ -203,9 +203,21 @@ def kernel_work(name, a):
     return "hbm", 0.0
 
 
+def profile_key(name, ints):
+    """The int arguments that identify a launch shape (drops per-call values: optimiser step, RNG stream id)."""
+    if name == "mip360_adamw_pack":
+        return ints[:2]
+    if name == "mip360_level0_sample":
+        return ints[-2:]
+    if name == "mip360_resample_sample":
+        return ints[-3:]
+    return ints
+
+
 def summarise_profile(prof, steps, pk):
     agg = {}
     for name, ints, e0, e1 in prof:
+        ints = profile_key(name, ints)
         key = (name, ints)
         ms = e0.elapsed_time(e1)
         d = agg.setdefault(key, [0.0, 0])

@@ -379,7 +379,13 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
     rg_weights<E>(r, gl, head_mode, density_mode, density_bias);
     if (weights && active) rg_store<E>(weights + ray * N + j0, r.w);
     if (weights_only) continue;
-    if (s_vals && active) {  // model.py:196 fused: the lane's knots j0 .. j0+E-1 (the last lane also writes knot N)
+    if (!WO && s_vals) {
+      // model.py:196 fused: the lane's knots j0 .. j0+E-1 (the last lane also knot N).  The 16 rays of a block are one
+      // contiguous run of 16 (N+1) floats in s_vals / t_shift: the lanes park their blocked values in shared memory and
+      // the block stores the run with fully coalesced 4-byte stores (a lane's own blocked stores would touch 8 sectors
+      // per ray and instruction)
+      __shared__ float s_tile[2][RG_RAYS_PER_BLOCK * (N + 1)];
+      const int g = threadIdx.x >> 3;
       const int nk = E + (gl == RG_LANES - 1 ? 1 : 0);
       const TToS tr = t_to_s_ray(nr, fr);
 #pragma unroll
@@ -387,10 +393,20 @@ composite_fwd_rg_kernel(const float* __restrict__ rgb_or_raw, const float* __res
         if (i < nk) {
           float sv, ts;
           t_to_s_one(r.t[i], tr, sv, ts);
-          s_vals[ray * (N + 1) + j0 + i] = sv;
-          if (t_shift) t_shift[ray * (N + 1) + j0 + i] = ts;
+          s_tile[0][g * (N + 1) + j0 + i] = sv;
+          s_tile[1][g * (N + 1) + j0 + i] = ts;
         }
       }
+      __syncthreads();
+      const long long rays_here = (B - base) < RG_RAYS_PER_BLOCK ? (B - base) : RG_RAYS_PER_BLOCK;
+      const int run = (int)rays_here * (N + 1);
+      float* gs = s_vals + base * (N + 1);
+      for (int idx = threadIdx.x; idx < run; idx += RG_THREADS) gs[idx] = s_tile[0][idx];
+      if (t_shift) {
+        float* gt = t_shift + base * (N + 1);
+        for (int idx = threadIdx.x; idx < run; idx += RG_THREADS) gt[idx] = s_tile[1][idx];
+      }
+      __syncthreads();
     }
     float a = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, wt = 0.f;
 #pragma unroll

@@ -68,3 +68,24 @@ def golden2():
 def rays_from(case, device="cpu"):
     from oracle.mip360_oracle import Rays
     return Rays(*[case[k].to(device) for k in Rays._fields])
+
+
+# ---------------------------------------------------------------------------------------------------
+# measured parity margins: tests call parity_record(name, value); the session writes the worst value per name to
+# gpurun_out/parity.json (copied to profiles/rNN_parity.json).  Tolerances in the tests are <= 2x these records.
+# ---------------------------------------------------------------------------------------------------
+_PARITY = {}
+
+
+def parity_record(name, value):
+    v = float(value)
+    _PARITY[name] = max(_PARITY.get(name, 0.0), v)
+    return v
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if _PARITY and torch.cuda.is_available():
+        import json
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        json.dump(dict(sorted(_PARITY.items())), open(os.path.join(out, "parity.json"), "w"), indent=1)

@@ -13,7 +13,7 @@ import math
 import pytest
 import torch
 
-from conftest import rays_from
+from conftest import parity_record, rays_from
 from oracle import mip360_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -420,9 +420,16 @@ def test_cast_weight_and_adamw(ops):
 # ---------------------------------------------------------------------------------------------------
 # whole model: golden (tiny widths) and default widths against the oracle
 # ---------------------------------------------------------------------------------------------------
+# bf16-MLP margins at B = 256 rays (default widths): 2 x the worst value recorded on the B200 (profiles/r02_parity.json)
+TOL_B256 = dict(loss_prop=2.5e-3, loss_nerf=1e-4, loss_dist=3e-4, grad=1e-1)  # recorded: 1.1e-3, 1.0e-5, 9.5e-5, 4.97e-2
+
+
 def _grad_rel(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+TOL_GOLDEN_GRAD = 6e-2  # tiny-width literal-reference fixture (B = 4, widths 16 / 32): 2 x the recorded worst (2.9e-2)
 
 
 def _model_from_sd(sd, N, HP, HN, randomized):
@@ -462,9 +469,9 @@ def test_golden_model_bf16(golden):
     gp = torch.autograd.grad(lp, list(m.prop_net.parameters()), retain_graph=True)
     gn = torch.autograd.grad(ln + 0.01 * ld, list(m.nerf_net.parameters()))
     for (k, _), gr in list(zip(m.prop_net.named_parameters(), gp)):
-        assert _grad_rel(gr, c["grad.prop_net." + k]) < 6e-2, k
+        assert parity_record("golden_tiny/grad_rel_worst", _grad_rel(gr, c["grad.prop_net." + k])) < TOL_GOLDEN_GRAD, k
     for (k, _), gr in list(zip(m.nerf_net.named_parameters(), gn)):
-        assert _grad_rel(gr, c["grad.nerf_net." + k]) < 6e-2, k
+        assert parity_record("golden_tiny/grad_rel_worst", _grad_rel(gr, c["grad.nerf_net." + k])) < TOL_GOLDEN_GRAD, k
     out = m(rays)
     close(out[0], c["fwd_rgb"], rtol=2e-2, atol=5e-3)
 
@@ -517,16 +524,20 @@ def test_default_model_vs_oracle():
     lp = Loss_prop(t_shift, w.detach(), t_hat, w_hat)
     ln, _ = Loss_nerf(rgb, pixels.to(DEV))
     ld = Loss_dist(s, w)
-    close(lp, lp_r, rtol=1e-1, atol=1e-3, msg="loss_prop")
-    close(ln, ln_r, rtol=2e-2, atol=5e-2, msg="loss_nerf")
-    close(ld, ld_r, rtol=5e-2, atol=1e-4, msg="loss_dist")
+    relerr = lambda a, b: abs(float(a) - float(b)) / abs(float(b))
+    # tolerances = 2 x the recorded worst (profiles/r02_parity.json: B256/loss_*), rounded up
+    assert parity_record("B256/loss_prop_rel", relerr(lp, lp_r)) < TOL_B256["loss_prop"]
+    assert parity_record("B256/loss_nerf_rel", relerr(ln, ln_r)) < TOL_B256["loss_nerf"]
+    assert parity_record("B256/loss_dist_rel", relerr(ld, ld_r)) < TOL_B256["loss_dist"]
     gp = torch.autograd.grad(lp, list(m.prop_net.parameters()))
     gn = torch.autograd.grad(ln + 0.01 * ld, list(m.nerf_net.parameters()))
     worst = 0.0
     for k, gr, ref in list(zip(names_p, gp, gp_r)) + list(zip(names_n, gn, gn_r)):
         rel = _grad_rel(gr, ref)
         worst = max(worst, rel)
-        assert rel < 1e-1, (k, rel)
+        parity_record("B256/grad_rel/" + k, rel)
+        assert rel < TOL_B256["grad"], (k, rel)
+    parity_record("B256/grad_rel_worst", worst)
     print("worst relative gradient error (bf16 MLP vs fp32 oracle):", worst)
     # plain forward through the public entry point, eval flag plumbing (App. A7)
     m.eval()  # eval() -> nn.Module.eval() -> self.train(False) -> resets the flag: still True afterwards (App. A7)

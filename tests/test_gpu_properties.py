@@ -4,6 +4,8 @@ and a short training run through the public Trainer."""
 import pytest
 import torch
 
+from conftest import parity_record
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 B, N = 16384, 64
@@ -238,11 +240,19 @@ def test_kernel_variants_agree(ops):
         torch.testing.assert_close(fast[k], slow[k], rtol=1e-4, atol=1e-4 * math.sqrt(M))
 
 
+# full size (16 384 rays x 64 samples): 2 x the worst values recorded on the B200 (profiles/r02_parity.json: full/*)
+# recorded: losses prop 1.0e-3 / nerf 1.9e-5 / dist 9.5e-5, worst gradient 0.98e-2, outputs max |err| rgb 1.6e-3, w_hat 1.5e-3,
+# acc 2.0e-4, w 7.6e-5, mean |err| rgb 3.7e-4
+TOL_FULL_LOSS = dict(loss_prop=2.5e-3, loss_nerf=1e-4, loss_dist=3e-4)
+TOL_FULL_GRAD = 2e-2
+TOL_FULL_OUT = dict(w_hat=(3e-3, 5e-5), rgb=(4e-3, 8e-4), acc=(4e-4, 2e-5), w=(2e-4, 1e-5))  # (max, mean) absolute error
+
+
 def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu():
     """BASELINE size (16 384 rays x 64 samples, default widths): the bf16 tcgen05 path against the fp32 oracle
     evaluated ON THE GPU (plain torch fp32 ops, TF32 off) with the same weights and the same random draws.
-    Stated bf16 tolerances: per-ray outputs |err| <= 2e-2, mean |err| <= 2e-3; losses 2 %; per-tensor gradient
-    relative Frobenius error <= 6 %."""
+    Stated bf16 tolerances = 2 x the worst values recorded on the B200 (profiles/r02_parity.json): per-ray outputs
+    max |err| <= 4e-3 (rgb), losses 0.25 % (proposal) / 0.01-0.03 %, per-tensor gradient relative Frobenius error <= 2 %."""
     from mipnerf360_b200 import mlp as MLP
     from mipnerf360_b200 import ops
     from mipnerf360_b200.intern.loss import Loss_dist, Loss_nerf, Loss_prop
@@ -293,19 +303,25 @@ def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu():
     s, t_shift = ops.t_to_s(new_t, rays.near, rays.far)
     for name, a, b in (("w_hat", w_hat, w_hat_r), ("rgb", rgb, rgb_r), ("acc", acc, acc_r), ("w", w, w_r)):
         err = (a.detach() - b).abs()
-        assert float(err.max()) <= 2e-2 and float(err.mean()) <= 2e-3, (name, float(err.max()), float(err.mean()))
+        parity_record(f"full/{name}_max_abs", err.max())
+        parity_record(f"full/{name}_mean_abs", err.mean())
+        assert float(err.max()) <= TOL_FULL_OUT[name][0] and float(err.mean()) <= TOL_FULL_OUT[name][1], \
+            (name, float(err.max()), float(err.mean()))
     lp = Loss_prop(t_shift, w.detach(), t_hat, w_hat)
     ln, _ = Loss_nerf(rgb, pixels)
     ld = Loss_dist(s, w)
     for name, a, b in (("loss_prop", lp, lp_r), ("loss_nerf", ln, ln_r), ("loss_dist", ld, ld_r)):
-        assert abs(float(a) - float(b)) <= 2e-2 * abs(float(b)) + 1e-4, (name, float(a), float(b))
+        parity_record(f"full/{name}_rel", abs(float(a) - float(b)) / abs(float(b)))
+        assert abs(float(a) - float(b)) <= TOL_FULL_LOSS[name] * abs(float(b)), (name, float(a), float(b))
     gp = torch.autograd.grad(lp, list(m.prop_net.parameters()))
     gn = torch.autograd.grad(ln + 0.01 * ld, list(m.nerf_net.parameters()))
     worst = 0.0
     for k, a, b in list(zip(names_p, gp, gp_r)) + list(zip(names_n, gn, gn_r)):
         rel = float((a - b).norm() / (b.norm() + 1e-20))
         worst = max(worst, rel)
-        assert rel <= 6e-2, (k, rel)
+        parity_record("full/grad_rel/" + k, rel)
+        assert rel <= TOL_FULL_GRAD, (k, rel)
+    parity_record("full/grad_rel_worst", worst)
     print("full-size worst relative gradient error:", worst)
 
 
