@@ -45,7 +45,9 @@ void mip360_reset_launch_count(void);
 /* Runtime switch between kernel variants that compute the same function (used by the tests to compare them):
  * key 0 = 8-lanes-per-ray register kernels for N in {32,64,128} (else one warp per ray),
  * key 1 = CTA-pair (cta_group::2) GEMM tiles, key 2 = short-K two-CTAs-per-SM GEMM configuration,
- * key 3 = packed (fp32x2 / bf16x2) arithmetic in the ReLU and trunk-Sigmoid GEMM epilogues.  All default on. */
+ * key 3 = packed (fp32x2 / bf16x2) arithmetic in the ReLU and trunk-Sigmoid GEMM epilogues, key 4 = the layer-fused
+ * forward of the proposal MLP (mip360_mlp_fwd_fused_narrow; off = it reports MIP360_ERR_UNSUPPORTED and the caller runs
+ * the layers one by one).  All default on. */
 int mip360_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -285,6 +287,13 @@ typedef struct mip360_layer {
  *   for the head, all ACCUMULATED into (split-K atomics).  dz_head [M,64], dz0, dz1 [M, max n_pad]: bf16 scratch. */
 int mip360_mlp_fwd(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const mip360_layer* head,
                    int n_valid, uint16_t* const* acts, int n_act_bufs, float* out, mip360_stream_t stream);
+/* mip360_mlp_fwd for the proposal net's shape — x [M,64] -> 4 layers of width 256 (ReLU / Sigmoid) -> head [64 padded, 256]
+ * without activation — as ONE persistent kernel: a 128-row tile's activations stay in shared memory (written by the epilogue
+ * in the UMMA operand layout) and tensor memory, weights are streamed from L2.  acts: NULL (inference) or 4 buffers
+ * [M,256] that receive the trunk activations for the backward pass.  Bit-identical to the layer-by-layer path.  Other
+ * shapes: MIP360_ERR_UNSUPPORTED. */
+int mip360_mlp_fwd_fused_narrow(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const mip360_layer* head,
+                                int n_valid, uint16_t* const* acts, float* out, mip360_stream_t stream);
 /* mip360_mlp_fwd with the head folded into the last trunk layer (mip360_linear_fwd_head): head_w4 fp32 [k_pad, 4].
  * `out` [M,4] receives the head's PRE-activation sums WITHOUT bias (zeroed inside).  With n_act_bufs == 2 the last trunk
  * activation is not written at all. */

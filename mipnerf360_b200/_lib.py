@@ -66,6 +66,7 @@ SIGNATURES = {
     "mip360_linear_wgrad": [P, P, c_int, c_int, c_int, P, P, P],
     "mip360_cast_weight": [P, c_int, c_int, c_int, c_int, P, P, P],
     "mip360_mlp_fwd": [P, c_int, P, c_int, P, c_int, P, c_int, P, P],
+    "mip360_mlp_fwd_fused_narrow": [P, c_int, P, c_int, P, c_int, P, P, P],
     "mip360_mlp_fwd_fused_head": [P, c_int, P, c_int, P, P, c_int, P, P],
     "mip360_mlp_bwd_fused_head": [P, P, c_int, P, c_int, P, P, P, P, P, P, P],
     "mip360_mlp_bwd": [P, P, P, c_int, P, c_int, P, c_int, P, P, P, P, P, P, P],
@@ -157,6 +158,30 @@ def call(name, *args):
         raise Mip360Error(f"{name} failed ({rc}): {lib.mip360_last_error().decode()}")
 
 
+ERR_UNSUPPORTED = -3
+
+
+def call_rc(name, *args):
+    """Like call(), but a MIP360_ERR_UNSUPPORTED result is returned (True = ran, False = shape not covered by this entry
+    point) instead of raised: for optional fast paths with a general fallback."""
+    lib = load()
+    if PROFILE is None:
+        rc = getattr(lib, name)(*args, stream())
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        if rc == 0:
+            PROFILE.append((name, tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and a < (1 << 31)),
+                            e0, e1))
+    if rc == ERR_UNSUPPORTED:
+        return False
+    if rc != 0:
+        raise Mip360Error(f"{name} failed ({rc}): {lib.mip360_last_error().decode()}")
+    return True
+
+
 def check_cuda(*tensors, dtype=torch.float32):
     """The product path runs on the GPU only: reject CPU tensors loudly instead of falling back."""
     for t in tensors:
@@ -183,7 +208,7 @@ def reset_launch_count():
     load().mip360_reset_launch_count()
 
 
-OPT_RAY_GROUP, OPT_CTA_PAIR, OPT_SHORT_K, OPT_PACKED_EPILOGUE = 0, 1, 2, 3
+OPT_RAY_GROUP, OPT_CTA_PAIR, OPT_SHORT_K, OPT_PACKED_EPILOGUE, OPT_FUSED_NARROW = 0, 1, 2, 3, 4
 
 
 def set_option(key, value):

@@ -14,7 +14,7 @@ namespace mip360 {
 void set_error(const char* fmt, ...);
 // runtime switches between kernel variants (mip360_set_option): every variant computes the same function, the
 // switches exist so that tests can compare them against each other
-enum { OPT_RAY_GROUP = 0, OPT_CTA_PAIR = 1, OPT_SHORT_K = 2, OPT_PACKED_EPILOGUE = 3, OPT_COUNT = 4 };
+enum { OPT_RAY_GROUP = 0, OPT_CTA_PAIR = 1, OPT_SHORT_K = 2, OPT_PACKED_EPILOGUE = 3, OPT_FUSED_NARROW = 4, OPT_COUNT = 5 };
 bool option(int key);
 void count_launch(int n = 1);
 constexpr int MAX_DEVICES = 64;

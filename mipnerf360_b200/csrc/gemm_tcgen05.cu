@@ -907,8 +907,29 @@ adamw_pack_kernel(const mip360_pack_entry* __restrict__ entries, int n_entries, 
 // replaces head_grad_pack + the 64-column head wgrad and dgrad GEMMs, which read Y twice and move a [M, 64] bf16
 // gradient besides.  HBM-bound: 2N bytes read + 2N written + 16 per row.  A thread owns 8 columns (16-byte loads and
 // stores), a block walks rows in a grid-stride loop with the weight gradient in registers and flushes it once.
+// fp32 pair helpers (one instruction for two lanes of arithmetic: the kernel below is bound by instruction issue at the
+// power-capped clock, not by HBM, unless its FMAs are packed)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 template <int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const uint16_t* __restrict__ Y, long long M,
                 int N, uint16_t* __restrict__ dZ, float* __restrict__ dWh, int ldw, float* __restrict__ dbh) {
   const int cols8 = N >> 3;                       // 16-byte column groups per row
@@ -916,18 +937,21 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
   const int rows_per_pass = blockDim.x / cols8;   // rows a block covers per step
   const int rsub = threadIdx.x / cols8;
   const int c0 = cg * 8;
-  float w[8][4];
+  // head weights of the thread's 8 columns as column PAIRS per head: wp[q][h] = (w[2q][h], w[2q+1][h])
+  uint64_t wp[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(w4) + c0 + i);
-    w[i][0] = v.x; w[i][1] = v.y; w[i][2] = v.z; w[i][3] = v.w;
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w4) + c0 + 2 * q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w4) + c0 + 2 * q + 1);
+    wp[q][0] = f2_pack(a.x, b.x); wp[q][1] = f2_pack(a.y, b.y); wp[q][2] = f2_pack(a.z, b.z); wp[q][3] = f2_pack(a.w, b.w);
   }
-  float acc[8][4];
+  uint64_t acc[4][4];  // weight-gradient partial sums, same pairing
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int h = 0; h < 4; ++h) acc[i][h] = 0.f;
+    for (int h = 0; h < 4; ++h) acc[q][h] = 0ull;
   float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint64_t one2 = f2_pack(1.f, 1.f), neg2 = f2_pack(-1.f, -1.f);
   if (rsub < rows_per_pass) {
     const long long stride = (long long)gridDim.x * rows_per_pass;
     constexpr int U = 4;  // rows in flight per thread: all loads of a step are issued before the arithmetic
@@ -947,38 +971,280 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
         const long long r = r0 + u * stride;
         if (r >= M) break;
         const uint32_t yw[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+        const uint64_t g0 = f2_pack(gr[u].x, gr[u].x), g1 = f2_pack(gr[u].y, gr[u].y), g2 = f2_pack(gr[u].z, gr[u].z),
+                       g3 = f2_pack(gr[u].w, gr[u].w);
         uint32_t out[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float res[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = 2 * q + e;
-            const float y = e == 0 ? __uint_as_float(yw[q] << 16) : __uint_as_float(yw[q] & 0xffff0000u);
-            const float dz = gr[u].x * w[i][0] + gr[u].y * w[i][1] + gr[u].z * w[i][2] + gr[u].w * w[i][3];
-            float d = 1.f;
-            if (ACT == ACT_RELU) d = y > 0.f ? 1.f : 0.f;
-            else if (ACT == ACT_SIGMOID) d = y * (1.f - y);
-            res[e] = dz * d;
-            acc[i][0] = fmaf(gr[u].x, y, acc[i][0]);
-            acc[i][1] = fmaf(gr[u].y, y, acc[i][1]);
-            acc[i][2] = fmaf(gr[u].z, y, acc[i][2]);
-            acc[i][3] = fmaf(gr[u].w, y, acc[i][3]);
+          const uint64_t y2 = f2_pack(__uint_as_float(yw[q] << 16), __uint_as_float(yw[q] & 0xffff0000u));
+          // dz pair = sum_h g_h * (w[2q][h], w[2q+1][h])
+          uint64_t dz = f2_mul(g0, wp[q][0]);
+          dz = f2_fma(g1, wp[q][1], dz);
+          dz = f2_fma(g2, wp[q][2], dz);
+          dz = f2_fma(g3, wp[q][3], dz);
+          // weight gradient: acc[q][h] += g_h * (y[2q], y[2q+1])
+          acc[q][0] = f2_fma(g0, y2, acc[q][0]);
+          acc[q][1] = f2_fma(g1, y2, acc[q][1]);
+          acc[q][2] = f2_fma(g2, y2, acc[q][2]);
+          acc[q][3] = f2_fma(g3, y2, acc[q][3]);
+          float lo, hi;
+          if (ACT == ACT_SIGMOID) {
+            dz = f2_mul(dz, f2_mul(y2, f2_fma(y2, neg2, one2)));  // * y (1 - y)
+            f2_unpack(dz, lo, hi);
+          } else {
+            f2_unpack(dz, lo, hi);
+            if (ACT == ACT_RELU) {
+              float ylo, yhi;
+              f2_unpack(y2, ylo, yhi);
+              lo = ylo > 0.f ? lo : 0.f;
+              hi = yhi > 0.f ? hi : 0.f;
+            }
           }
-          out[q] = pack_bf16x2(res[0], res[1]);
+          out[q] = pack_bf16x2(lo, hi);
         }
         *reinterpret_cast<uint4*>(dZ + r * N + c0) = make_uint4(out[0], out[1], out[2], out[3]);
         if (cg == 0) { gsum[0] += gr[u].x; gsum[1] += gr[u].y; gsum[2] += gr[u].z; gsum[3] += gr[u].w; }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int h = 0; h < 4; ++h) atomicAdd(dWh + (long long)h * ldw + c0 + i, acc[i][h]);
+      for (int h = 0; h < 4; ++h) {
+        float lo, hi;
+        f2_unpack(acc[q][h], lo, hi);
+        atomicAdd(dWh + (long long)h * ldw + c0 + 2 * q, lo);
+        atomicAdd(dWh + (long long)h * ldw + c0 + 2 * q + 1, hi);
+      }
     if (cg == 0 && dbh) {
 #pragma unroll
       for (int h = 0; h < 4; ++h) atomicAdd(dbh + h, gsum[h]);
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Layer-fused forward of a narrow MLP (the proposal net, model.py:43-53,91): K0 -> W -> W -> W -> W -> head, W = 256.
+// One persistent CTA per SM walks 128-row tiles; a tile's activations never leave the SM:
+//   warp 0      TMA: the tile's input rows [128 x K0] and, layer by layer, the weights as [N x 64] K-chunks (from L2)
+//   warp 1      one lane issues tcgen05.mma; the A operand of layer s >= 1 is the previous layer's output, written by
+//               the epilogue warps into shared memory in the UMMA K-major 128-byte-swizzled layout ([128 x 64] chunks)
+//   warps 2-5   epilogue: TMEM accumulator -> bias + ReLU / Sigmoid -> bf16 -> activation buffer (and, when the
+//               activations are needed for the backward pass, a TMA store of the same 4 KB box to HBM)
+// Pipelining inside a tile: layer s+1's k-chunk j only needs output columns [64j, 64j+64) of layer s, so its MMAs start
+// as soon as the epilogue has written that chunk (per-chunk mbarriers); layers alternate between two TMEM accumulators
+// and two activation buffers.  Arithmetic (MMA order, epilogue) is that of linear_kernel: results are bit-identical to
+// the layer-by-layer path.
+// ---------------------------------------------------------------------------------------------
+constexpr int PF_W = 256;        // trunk width
+constexpr int PF_TRUNK = 4;      // trunk layers
+constexpr int PF_STAGES = 2;     // weight ring
+struct PropFusedCfg {
+  static constexpr int X_BYTES = BM * BK * 2;                    // 16 KB (K0 = 64)
+  static constexpr int ACT_BYTES = BM * PF_W * 2;                // 64 KB: 4 chunks of [128 x 64]
+  static constexpr int W_STAGE_BYTES = PF_W * BK * 2;            // 32 KB
+  static constexpr int BIAS_BYTES = (PF_TRUNK * PF_W + 64) * 4;  // 4 trunk biases + padded head bias
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = X_BYTES + 2 * ACT_BYTES + PF_STAGES * W_STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "fused proposal MLP exceeds shared memory");
+};
+struct PropFusedParams {
+  const float* bias[PF_TRUNK + 1];  // [256] x 4, head [64]
+  int act[PF_TRUNK];                // ACT_RELU / ACT_SIGMOID_FAST
+  float* out;                       // [M, n_valid] fp32 head outputs (no activation)
+  int M, n_valid, save_acts;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w0,
+                      const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                      const __grid_constant__ CUtensorMap tmap_w3, const __grid_constant__ CUtensorMap tmap_wh,
+                      const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                      const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_a3,
+                      const PropFusedParams p) {
+  using Cfg = PropFusedCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xbuf = smem_base;
+  const uint32_t actbuf = xbuf + Cfg::X_BYTES;                       // 2 x 64 KB
+  const uint32_t wring = actbuf + 2 * Cfg::ACT_BYTES;                // PF_STAGES x 32 KB
+  const uint32_t bias_smem = wring + PF_STAGES * Cfg::W_STAGE_BYTES;
+  const uint32_t bar_base = bias_smem + Cfg::BIAS_BYTES;
+  auto w_full = [&](int s) { return bar_base + 8u * s; };
+  auto w_empty = [&](int s) { return bar_base + 8u * (PF_STAGES + s); };
+  const uint32_t x_full = bar_base + 8u * (2 * PF_STAGES), x_empty = x_full + 8u;
+  auto act_ready = [&](int b, int j) { return bar_base + 8u * (2 * PF_STAGES + 2 + 4 * b + j); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 10 + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 12 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * PF_STAGES + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (p.M + BM - 1) / BM;
+  const CUtensorMap* tmap_w[PF_TRUNK + 1] = {&tmap_w0, &tmap_w1, &tmap_w2, &tmap_w3, &tmap_wh};
+  const CUtensorMap* tmap_a[PF_TRUNK] = {&tmap_a0, &tmap_a1, &tmap_a2, &tmap_a3};
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PF_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    for (int b = 0; b < 2; ++b)
+      for (int j = 0; j < 4; ++j) mbar_init(act_ready(b, j), 4);  // one arrival per epilogue warp
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4); }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s <= PF_TRUNK; ++s) prefetch_tmap(tmap_w[s]);
+  }
+  // biases of every layer into shared memory (read back as broadcasts by the epilogue)
+  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += GEMM_THREADS) {
+    const int l = i < PF_TRUNK * PF_W ? i / PF_W : PF_TRUNK;
+    const int c = i - l * PF_W;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(__ldg(p.bias[l] + c)) : "memory");
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: input rows of the tile, then the weights of the five GEMM stages as K-chunks =====
+      uint32_t ws = 0, wphase = 0, xphase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(x_empty, xphase ^ 1u);
+        mbar_arrive_expect_tx(x_full, Cfg::X_BYTES);
+        tma_load_2d(xbuf, &tmap_x, x_full, 0, tile * BM);
+        xphase ^= 1u;
+        for (int s = 0; s <= PF_TRUNK; ++s) {
+          const int kc = s == 0 ? 1 : PF_W / BK;
+          const uint32_t bytes = (uint32_t)(s < PF_TRUNK ? PF_W : 64) * BK * 2;
+          for (int j = 0; j < kc; ++j) {
+            mbar_wait(w_empty(ws), wphase ^ 1u);
+            mbar_arrive_expect_tx(w_full(ws), bytes);
+            tma_load_2d(wring + ws * Cfg::W_STAGE_BYTES, tmap_w[s], w_full(ws), j * BK, 0);
+            if (++ws == PF_STAGES) { ws = 0; wphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_trunk = make_idesc_bf16(PF_W, 0, 0, BM);
+      constexpr uint32_t idesc_head = make_idesc_bf16(64, 0, 0, BM);
+      uint32_t ws = 0, wphase = 0, xphase = 0;
+      uint32_t acc_uses[2] = {0, 0};   // completed uses of each accumulator (phase of acc_empty)
+      uint32_t fills[2] = {0, 0};      // fills of each activation buffer consumed so far (phase of act_ready)
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int s = 0; s <= PF_TRUNK; ++s) {
+          const int ab = s & 1;
+          mbar_wait(acc_empty(ab), (acc_uses[ab] & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * PF_W;
+          const int kc = s == 0 ? 1 : PF_W / BK;
+          const int ib = (s - 1) & 1;  // activation buffer holding this stage's input (s >= 1)
+          for (int j = 0; j < kc; ++j) {
+            mbar_wait(w_full(ws), wphase);
+            if (s == 0) mbar_wait(x_full, xphase);
+            else mbar_wait(act_ready(ib, j), fills[ib] & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = s == 0 ? xbuf : actbuf + ib * Cfg::ACT_BYTES + j * (BM * BK * 2);
+            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(wring + ws * Cfg::W_STAGE_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16<1>(d_tmem, adesc + 2u * k, bdesc + 2u * k, s < PF_TRUNK ? idesc_trunk : idesc_head,
+                           (j | k) != 0 ? 1u : 0u);
+            umma_commit<1>(w_empty(ws));
+            if (++ws == PF_STAGES) { ws = 0; wphase ^= 1u; }
+          }
+          if (s == 0) {
+            umma_commit<1>(x_empty);  // the input rows may be replaced by the next tile's
+            xphase ^= 1u;
+          } else {
+            ++fills[ib];
+          }
+          umma_commit<1>(acc_full(ab));
+          ++acc_uses[ab];
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32) =====
+    const int q = warp & 3;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint32_t acc_seen[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = tile * BM;
+      const int row = m0 + q * 32 + lane;
+      for (int s = 0; s <= PF_TRUNK; ++s) {
+        const int ab = s & 1;
+        mbar_wait(acc_full(ab), acc_seen[ab] & 1u);
+        ++acc_seen[ab];
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ab * PF_W;
+        if (s < PF_TRUNK) {
+          const int ob = s & 1;  // output buffer = input of stage s + 1
+          const uint32_t bsm = bias_smem + 4u * (s * PF_W);
+          if (p.save_acts && lane == 0) tma_store_wait_read<0>();  // boxes of this buffer stored two stages ago are free
+          __syncwarp();
+#pragma unroll 1
+          for (int jj = 0; jj < PF_W / 64; ++jj) {
+            const uint32_t box = actbuf + ob * Cfg::ACT_BYTES + jj * (BM * BK * 2) + q * (32 * 128);
+            uint32_t packed[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
+              tmem_ld_wait();
+              if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
+              else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              st_shared_v4(box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.save_acts) {
+                tma_store_2d(tmap_a[s], box, jj * 64, m0 + q * 32);
+                tma_store_commit();
+              }
+              mbar_arrive(act_ready(ob, jj));
+            }
+          }
+        } else {
+          // head: n_valid <= 8 real columns, no activation (model.py:91: softplus follows in the compositing kernel)
+          uint32_t v8[8];
+          tmem_ld_32x8(t_row, v8);
+          tmem_ld_wait();
+          if (row < p.M) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float bv;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(bias_smem + 4u * (PF_TRUNK * PF_W + i)));
+              if (i < p.n_valid) p.out[(size_t)row * p.n_valid + i] = __uint_as_float(v8[i]) + bv;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(ab));
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
@@ -1081,6 +1347,43 @@ static int dispatch_linear(const uint16_t* A, const uint16_t* Bw, const uint16_t
   return MIP360_ERR_UNSUPPORTED;
 }
 
+static int launch_prop_fused(const uint16_t* x, int M, const mip360_layer* trunk, const mip360_layer* head, int n_valid,
+                             uint16_t* const* acts, float* out, cudaStream_t stream) {
+  using Cfg = PropFusedCfg;
+  static bool configured[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    MIP_CUDA(cudaFuncSetAttribute(prop_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  CUtensorMap tx, tw[PF_TRUNK + 1], ta[PF_TRUNK];
+  int rc;
+  if ((rc = make_tmap(&tx, x, M, BK, BM)) != MIP360_OK) return rc;
+  for (int l = 0; l < PF_TRUNK; ++l)
+    if ((rc = make_tmap(&tw[l], trunk[l].W, PF_W, trunk[l].k_pad, PF_W)) != MIP360_OK) return rc;
+  if ((rc = make_tmap(&tw[PF_TRUNK], head->W, 64, PF_W, 64)) != MIP360_OK) return rc;
+  for (int l = 0; l < PF_TRUNK; ++l) {
+    ta[l] = tx;
+    if (acts && (rc = make_tmap(&ta[l], acts[l], M, PF_W, 32)) != MIP360_OK) return rc;
+  }
+  PropFusedParams p{};
+  for (int l = 0; l < PF_TRUNK; ++l) {
+    p.bias[l] = trunk[l].bias;
+    p.act[l] = trunk[l].act == ACT_SIGMOID ? ACT_SIGMOID_FAST : trunk[l].act;
+  }
+  p.bias[PF_TRUNK] = head->bias;
+  p.out = out;
+  p.M = M;
+  p.n_valid = n_valid;
+  p.save_acts = acts ? 1 : 0;
+  const int tiles = (M + BM - 1) / BM;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  prop_fused_fwd_kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw[0], tw[1], tw[2], tw[3], tw[4], ta[0], ta[1],
+                                                                        ta[2], ta[3], p);
+  MIP_LAUNCH_CHECK();
+  return MIP360_OK;
+}
+
 template <int BN, int CG>
 static int launch_wgrad(const uint16_t* dY, const uint16_t* X, WgradParams p, cudaStream_t stream) {
   using Cfg = WgradCfg<BN, CG>;
@@ -1139,6 +1442,25 @@ int mip360_linear_fwd(const uint16_t* X, const uint16_t* W, const float* bias, i
   const int act_k = (act == ACT_SIGMOID && !out_f32) ? ACT_SIGMOID_FAST : act;
   LinearParams p{bias, out_bf16, out_f32, M, N, K, act_k, n_valid, option(OPT_PACKED_EPILOGUE) ? 1 : 0};
   return dispatch_linear<EPI_FWD>(X, W, nullptr, p, (cudaStream_t)stream);
+}
+
+int mip360_mlp_fwd_fused_narrow(const uint16_t* x, int M, const mip360_layer* trunk, int n_trunk, const mip360_layer* head,
+                                int n_valid, uint16_t* const* acts, float* out, mip360_stream_t stream) {
+  MIP_REQUIRE(trunk && head && out, "mlp_fwd_fused_narrow: null pointer");
+  if (M <= 0) return MIP360_OK;
+  MIP_REQUIRE(x, "mlp_fwd_fused_narrow: null input");
+  bool ok = n_trunk == PF_TRUNK && head->n_pad == 64 && head->k_pad == PF_W && head->act == ACT_NONE && n_valid >= 1 &&
+            n_valid <= 8 && option(OPT_FUSED_NARROW);
+  for (int l = 0; ok && l < n_trunk; ++l)
+    ok = trunk[l].n_pad == PF_W && trunk[l].k_pad == (l == 0 ? BK : PF_W) && (trunk[l].act == ACT_RELU || trunk[l].act == ACT_SIGMOID) &&
+         trunk[l].W && trunk[l].bias;
+  if (!ok) {
+    set_error("mlp_fwd_fused_narrow: only 64 -> 256 x 4 (ReLU / Sigmoid) -> head without activation is fused");
+    return MIP360_ERR_UNSUPPORTED;
+  }
+  if (acts)
+    for (int l = 0; l < n_trunk; ++l) MIP_REQUIRE(acts[l], "mlp_fwd_fused_narrow: activation buffer %d is null", l);
+  return launch_prop_fused(x, M, trunk, head, n_valid, acts, out, (cudaStream_t)stream);
 }
 
 int mip360_linear_fwd_head(const uint16_t* X, const uint16_t* W, const float* bias, int M, int N, int K, int act,

@@ -8,7 +8,7 @@ namespace mip360 {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
-static std::atomic<int> g_options[OPT_COUNT] = {{1}, {1}, {1}, {1}};
+static std::atomic<int> g_options[OPT_COUNT] = {{1}, {1}, {1}, {1}, {1}};
 
 bool option(int key) { return key >= 0 && key < OPT_COUNT && g_options[key].load(std::memory_order_relaxed) != 0; }
 

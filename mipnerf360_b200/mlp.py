@@ -146,6 +146,12 @@ class PackedMLP:
         self.packed()
         return self._cstructs
 
+    def narrow_shape(self):
+        """The shape mip360_mlp_fwd_fused_narrow covers: 64 -> 256 x 4 -> head without activation (the proposal net)."""
+        layers, head = self.packed()
+        return (len(layers) == 4 and self.head_act == ACT_NONE and layers[0][0].shape == (256, 64)
+                and all(W.shape == (256, 256) for W, _, _ in layers[1:]) and head[0].shape == (64, 256))
+
     def head_bias(self):
         """Padded fp32 head bias [64] (first n_valid entries real), refreshed with the operands."""
         return self.packed()[1][2]
@@ -193,18 +199,30 @@ class _MLPFunction(torch.autograd.Function):
                       out.data_ptr())
             saved = [x] + bufs
         else:
-            # product path: the whole MLP is one call into the C ABI (mip360_mlp_fwd)
+            # product path: the whole MLP is one call into the C ABI
             trunk_arr, head = mlp.cstructs()
-            if need_grad:
-                bufs = [torch.empty((M, Wb.shape[0]), device=x.device, dtype=torch.bfloat16) for Wb, _, _ in layers]
-            else:
-                wmax = max(Wb.shape[0] for Wb, _, _ in layers)
-                bufs = [torch.empty((M, wmax), device=x.device, dtype=torch.bfloat16) for _ in range(2)]
             out = torch.empty((M, mlp.n_valid), device=x.device, dtype=torch.float32)
-            mlp.last_n_act_bufs = len(bufs)  # 2 = inference ping-pong, n_trunk = saved for backward
-            ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
-            _lib.call("mip360_mlp_fwd", x.data_ptr(), M, trunk_arr, L, ctypes.byref(head), mlp.n_valid, ptrs, len(bufs),
-                      out.data_ptr())
+            ran = False
+            if mlp.narrow_shape():
+                # proposal-net shape: ONE kernel for all layers, activations stay on chip (written to HBM only when the
+                # backward pass needs them); falls through when the library reports the shape / option as unsupported
+                bufs = [torch.empty((M, Wb.shape[0]), device=x.device, dtype=torch.bfloat16) for Wb, _, _ in layers] \
+                    if need_grad else []
+                ptrs = (ctypes.c_void_p * L)(*[b.data_ptr() for b in bufs]) if need_grad else None
+                ran = _lib.call_rc("mip360_mlp_fwd_fused_narrow", x.data_ptr(), M, trunk_arr, L, ctypes.byref(head),
+                                   mlp.n_valid, ptrs, out.data_ptr())
+                if ran:
+                    mlp.last_n_act_bufs = len(bufs)
+            if not ran:
+                if need_grad:
+                    bufs = [torch.empty((M, Wb.shape[0]), device=x.device, dtype=torch.bfloat16) for Wb, _, _ in layers]
+                else:
+                    wmax = max(Wb.shape[0] for Wb, _, _ in layers)
+                    bufs = [torch.empty((M, wmax), device=x.device, dtype=torch.bfloat16) for _ in range(2)]
+                mlp.last_n_act_bufs = len(bufs)  # 2 = inference ping-pong, n_trunk = saved for backward
+                ptrs = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+                _lib.call("mip360_mlp_fwd", x.data_ptr(), M, trunk_arr, L, ctypes.byref(head), mlp.n_valid, ptrs, len(bufs),
+                          out.data_ptr())
             saved = [x] + bufs
         if need_grad:
             ctx.mlp = mlp

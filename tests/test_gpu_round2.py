@@ -731,3 +731,58 @@ def test_graphed_render_chunks_equal_eager_chunks(ops):
     same_rays = O.Rays(*[x[:100].repeat(5, 1) for x in rays])  # five identical chunks must not render identically
     rr = render_rays(m, same_rays, 100)[0].view(5, 100, 3)
     assert not torch.equal(rr[2], rr[3]) and not torch.equal(rr[3], rr[4])
+
+
+def test_layer_fused_proposal_mlp_is_bit_identical_to_the_layer_by_layer_path():
+    """mip360_mlp_fwd_fused_narrow (one persistent kernel, activations chained through shared / tensor memory) against
+    the chain of per-layer GEMM launches: logits and every saved activation bit for bit, gradients through the saved
+    activations, ragged row counts, inference (nothing saved) and training."""
+    from mipnerf360_b200 import _lib, mlp as MLP
+    from mipnerf360_b200.model import prop_net
+    dev = torch.device(DEV)
+    torch.manual_seed(11)
+    net = prop_net(randomized=False, num_samples=64, hidden_proposal=256, device=dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.5, 0.5)  # non-trivial biases
+    pk = net._packed
+    assert pk.narrow_shape()
+    for M in (128, 1000, 128 * 148 + 77, 300000):
+        x = (torch.randn(M, 64, device=dev) * 0.7).bfloat16()
+        x[:, 58:] = 0
+        res = {}
+        for fused in (True, False):
+            _lib.set_option(_lib.OPT_FUSED_NARROW, fused)
+            try:
+                with torch.no_grad():
+                    out_inf = MLP.mlp_apply(pk, x)
+                n_inf = pk.last_n_act_bufs
+                out = MLP.mlp_apply(pk, x)
+                n_tr = pk.last_n_act_bufs
+                net.zero_grad()
+                (out * torch.linspace(-1, 1, M, device=dev)[:, None]).sum().backward()
+            finally:
+                _lib.set_option(_lib.OPT_FUSED_NARROW, True)
+            res[fused] = dict(out=out.detach().clone(), out_inf=out_inf.clone(),
+                              grads=[p.grad.clone() for p in net.parameters()], n=(n_inf, n_tr))
+        assert res[True]["n"] == (0, 4) and res[False]["n"] == (2, 4)   # fused inference keeps nothing in HBM
+        assert torch.equal(res[True]["out"], res[False]["out"]), M
+        assert torch.equal(res[True]["out_inf"], res[False]["out"]), M
+        for a, b in zip(res[True]["grads"], res[False]["grads"]):
+            # the saved activations are identical, so only split-K summation order differs
+            assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12
+    # against fp32 on bf16-rounded operands
+    M = 4096
+    x = (torch.randn(M, 64, device=dev) * 0.7).bfloat16()
+    x[:, 58:] = 0
+    with torch.no_grad():
+        out = MLP.mlp_apply(pk, x)
+        h = x.float()[:, :58]
+        for i, lin in enumerate([m for m in net.model if isinstance(m, torch.nn.Linear)]):
+            h = h @ lin.weight.bfloat16().float().t() + lin.bias
+            if i < 3:
+                h = torch.relu(h).bfloat16().float()
+            elif i == 3:
+                h = torch.sigmoid(h).bfloat16().float()
+    close(out, h, rtol=2e-2, atol=2e-2)
