@@ -1038,14 +1038,16 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
 // ---------------------------------------------------------------------------------------------
 constexpr int PF_W = 256;        // trunk width
 constexpr int PF_TRUNK = 4;      // trunk layers
-constexpr int PF_STAGES = 2;     // weight ring
+constexpr int PF_STAGES = 4;     // weight ring: 128 KB in flight hide the L2 latency of the 32 KB chunks
 struct PropFusedCfg {
   static constexpr int X_BYTES = BM * BK * 2;                    // 16 KB (K0 = 64)
   static constexpr int ACT_BYTES = BM * PF_W * 2;                // 64 KB: 4 chunks of [128 x 64]
   static constexpr int W_STAGE_BYTES = PF_W * BK * 2;            // 32 KB
   static constexpr int BIAS_BYTES = (PF_TRUNK * PF_W + 64) * 4;  // 4 trunk biases + padded head bias
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = X_BYTES + 2 * ACT_BYTES + PF_STAGES * W_STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  // ONE activation buffer: a layer's input is dead once its MMAs have completed, which is exactly when the epilogue starts
+  // to write that layer's output — in place, chunk by chunk, as the next layer's A operand
+  static constexpr int SMEM_BYTES = X_BYTES + ACT_BYTES + PF_STAGES * W_STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "fused proposal MLP exceeds shared memory");
 };
 struct PropFusedParams {
@@ -1066,17 +1068,17 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xbuf = smem_base;
-  const uint32_t actbuf = xbuf + Cfg::X_BYTES;                       // 2 x 64 KB
-  const uint32_t wring = actbuf + 2 * Cfg::ACT_BYTES;                // PF_STAGES x 32 KB
+  const uint32_t actbuf = xbuf + Cfg::X_BYTES;                       // 64 KB
+  const uint32_t wring = actbuf + Cfg::ACT_BYTES;                    // PF_STAGES x 32 KB
   const uint32_t bias_smem = wring + PF_STAGES * Cfg::W_STAGE_BYTES;
   const uint32_t bar_base = bias_smem + Cfg::BIAS_BYTES;
   auto w_full = [&](int s) { return bar_base + 8u * s; };
   auto w_empty = [&](int s) { return bar_base + 8u * (PF_STAGES + s); };
   const uint32_t x_full = bar_base + 8u * (2 * PF_STAGES), x_empty = x_full + 8u;
-  auto act_ready = [&](int b, int j) { return bar_base + 8u * (2 * PF_STAGES + 2 + 4 * b + j); };
-  auto acc_full = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 10 + a); };
-  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 12 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * PF_STAGES + 14);
+  auto act_ready = [&](int j) { return bar_base + 8u * (2 * PF_STAGES + 2 + j); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 6 + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * PF_STAGES + 8 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * PF_STAGES + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = (p.M + BM - 1) / BM;
@@ -1087,8 +1089,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int s = 0; s < PF_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
-    for (int b = 0; b < 2; ++b)
-      for (int j = 0; j < 4; ++j) mbar_init(act_ready(b, j), 4);  // one arrival per epilogue warp
+    for (int j = 0; j < 4; ++j) mbar_init(act_ready(j), 4);  // one arrival per epilogue warp
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4); }
     fence_barrier_init();
     prefetch_tmap(&tmap_x);
@@ -1138,7 +1139,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       constexpr uint32_t idesc_head = make_idesc_bf16(64, 0, 0, BM);
       uint32_t ws = 0, wphase = 0, xphase = 0;
       uint32_t acc_uses[2] = {0, 0};   // completed uses of each accumulator (phase of acc_empty)
-      uint32_t fills[2] = {0, 0};      // fills of each activation buffer consumed so far (phase of act_ready)
+      uint32_t fills = 0;              // fills of the activation buffer consumed so far (phase of act_ready)
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         for (int s = 0; s <= PF_TRUNK; ++s) {
           const int ab = s & 1;
@@ -1146,13 +1147,12 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ab * PF_W;
           const int kc = s == 0 ? 1 : PF_W / BK;
-          const int ib = (s - 1) & 1;  // activation buffer holding this stage's input (s >= 1)
           for (int j = 0; j < kc; ++j) {
             mbar_wait(w_full(ws), wphase);
             if (s == 0) mbar_wait(x_full, xphase);
-            else mbar_wait(act_ready(ib, j), fills[ib] & 1u);
+            else mbar_wait(act_ready(j), fills & 1u);
             tc_fence_after();
-            const uint32_t a_addr = s == 0 ? xbuf : actbuf + ib * Cfg::ACT_BYTES + j * (BM * BK * 2);
+            const uint32_t a_addr = s == 0 ? xbuf : actbuf + j * (BM * BK * 2);
             const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(wring + ws * Cfg::W_STAGE_BYTES, 16, 1024);
 #pragma unroll
@@ -1166,7 +1166,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             umma_commit<1>(x_empty);  // the input rows may be replaced by the next tile's
             xphase ^= 1u;
           } else {
-            ++fills[ib];
+            ++fills;
           }
           umma_commit<1>(acc_full(ab));
           ++acc_uses[ab];
@@ -1189,13 +1189,12 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + ab * PF_W;
         if (s < PF_TRUNK) {
-          const int ob = s & 1;  // output buffer = input of stage s + 1
           const uint32_t bsm = bias_smem + 4u * (s * PF_W);
-          if (p.save_acts && lane == 0) tma_store_wait_read<0>();  // boxes of this buffer stored two stages ago are free
+          if (p.save_acts && lane == 0) tma_store_wait_read<0>();  // the previous layer's boxes have been read by their stores
           __syncwarp();
 #pragma unroll 1
           for (int jj = 0; jj < PF_W / 64; ++jj) {
-            const uint32_t box = actbuf + ob * Cfg::ACT_BYTES + jj * (BM * BK * 2) + q * (32 * 128);
+            const uint32_t box = actbuf + jj * (BM * BK * 2) + q * (32 * 128);
             uint32_t packed[32];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -1215,7 +1214,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 tma_store_2d(tmap_a[s], box, jj * 64, m0 + q * 32);
                 tma_store_commit();
               }
-              mbar_arrive(act_ready(ob, jj));
+              mbar_arrive(act_ready(jj));
             }
           }
         } else {

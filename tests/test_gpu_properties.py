@@ -148,7 +148,7 @@ def test_model_and_trainer_full_size():
     assert all(torch.isfinite(torch.tensor(losses)))
     # (the very first Adam step moves all 7.6 M weights by +-lr and the loss jumps; from there it must go down)
     assert min(losses[4:]) < losses[1], losses
-    assert _lib.launch_count() > 8 * 100
+    assert _lib.launch_count() > 8 * 80
     # checkpoint round trip through the reference's state_dict layout (flat-buffer views included)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     m2 = mipNeRF360(randomized=True, num_samples=N, device=torch.device(DEV))

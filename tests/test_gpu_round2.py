@@ -760,18 +760,27 @@ def test_layer_fused_proposal_mlp_is_bit_identical_to_the_layer_by_layer_path():
                 n_inf = pk.last_n_act_bufs
                 out = MLP.mlp_apply(pk, x)
                 n_tr = pk.last_n_act_bufs
+                saved = [t.clone() for t in out.grad_fn.saved_tensors if t is not None]
                 net.zero_grad()
-                (out * torch.linspace(-1, 1, M, device=dev)[:, None]).sum().backward()
+                # positive row weights: the weight-gradient sums do not cancel, so their split-K reordering noise
+                # (atomics, run to run, on either path) stays ~1e-6 of the sum instead of being amplified
+                (out * torch.linspace(0.5, 1.5, M, device=dev)[:, None]).sum().backward()
             finally:
                 _lib.set_option(_lib.OPT_FUSED_NARROW, True)
-            res[fused] = dict(out=out.detach().clone(), out_inf=out_inf.clone(),
+            res[fused] = dict(out=out.detach().clone(), out_inf=out_inf.clone(), saved=saved,
                               grads=[p.grad.clone() for p in net.parameters()], n=(n_inf, n_tr))
         assert res[True]["n"] == (0, 4) and res[False]["n"] == (2, 4)   # fused inference keeps nothing in HBM
         assert torch.equal(res[True]["out"], res[False]["out"]), M
         assert torch.equal(res[True]["out_inf"], res[False]["out"]), M
+        assert len(res[True]["saved"]) == len(res[False]["saved"]) >= 5
+        for a, b in zip(res[True]["saved"], res[False]["saved"]):
+            assert a.shape == b.shape and torch.equal(a, b), M          # every activation the backward reads
         for a, b in zip(res[True]["grads"], res[False]["grads"]):
-            # the saved activations are identical, so only split-K summation order differs
-            assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12
+            # identical inputs to the same backward kernels: only the split-K atomics' order differs (bit-equal while
+            # one CTA owns a whole column sum, M <= 1000 here)
+            if M <= 1000:
+                assert torch.equal(a, b), M
+            assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-12, M
     # against fp32 on bf16-rounded operands
     M = 4096
     x = (torch.randn(M, 64, device=dev) * 0.7).bfloat16()
