@@ -1029,8 +1029,11 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
 //   warp 0      TMA: the tile's input rows [128 x K0] and, layer by layer, the weights as [N x 64] K-chunks (from L2)
 //   warp 1      one lane issues tcgen05.mma; the A operand of layer s >= 1 is the previous layer's output, written by
 //               the epilogue warps into shared memory in the UMMA K-major 128-byte-swizzled layout ([128 x 64] chunks)
-//   warps 2-5   epilogue: TMEM accumulator -> bias + ReLU / Sigmoid -> bf16 -> activation buffer (and, when the
-//               activations are needed for the backward pass, a TMA store of the same 4 KB box to HBM)
+//   warps 2-9   epilogue: TMEM accumulator -> bias + ReLU / Sigmoid -> bf16 -> activation buffer (and, when the
+//               activations are needed for the backward pass, a TMA store of the same 4 KB box to HBM).  A tile costs
+//               52 N=256 MMAs (~4.5 us) but four 128 x 256 epilogues, which four warps need ~10 us for (each waits out
+//               its own tcgen05.ld latencies): the kernel is epilogue-bound, so every TMEM lane quarter is served by
+//               TWO warps, one per pair of 64-column chunks
 // Pipelining inside a tile: layer s+1's k-chunk j only needs output columns [64j, 64j+64) of layer s, so its MMAs start
 // as soon as the epilogue has written that chunk (per-chunk mbarriers); layers alternate between two TMEM accumulators
 // and two activation buffers.  Arithmetic (MMA order, epilogue) is that of linear_kernel: results are bit-identical to
@@ -1039,6 +1042,8 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
 constexpr int PF_W = 256;        // trunk width
 constexpr int PF_TRUNK = 4;      // trunk layers
 constexpr int PF_STAGES = 4;     // weight ring: 128 KB in flight hide the L2 latency of the 32 KB chunks
+constexpr int PF_EPI_WARPS = 8;  // two per TMEM lane quarter
+constexpr int PF_THREADS = 64 + 32 * PF_EPI_WARPS;
 struct PropFusedCfg {
   static constexpr int X_BYTES = BM * BK * 2;                    // 16 KB (K0 = 64)
   static constexpr int ACT_BYTES = BM * PF_W * 2;                // 64 KB: 4 chunks of [128 x 64]
@@ -1057,7 +1062,7 @@ struct PropFusedParams {
   int M, n_valid, save_acts;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PF_THREADS, 1)
 prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w0,
                       const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                       const __grid_constant__ CUtensorMap tmap_w3, const __grid_constant__ CUtensorMap tmap_wh,
@@ -1089,14 +1094,14 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int s = 0; s < PF_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
-    for (int j = 0; j < 4; ++j) mbar_init(act_ready(j), 4);  // one arrival per epilogue warp
-    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4); }
+    for (int j = 0; j < 4; ++j) mbar_init(act_ready(j), 4);  // one arrival per TMEM lane quarter
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), PF_EPI_WARPS); }
     fence_barrier_init();
     prefetch_tmap(&tmap_x);
     for (int s = 0; s <= PF_TRUNK; ++s) prefetch_tmap(tmap_w[s]);
   }
   // biases of every layer into shared memory (read back as broadcasts by the epilogue)
-  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += GEMM_THREADS) {
+  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += PF_THREADS) {
     const int l = i < PF_TRUNK * PF_W ? i / PF_W : PF_TRUNK;
     const int c = i - l * PF_W;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(__ldg(p.bias[l] + c)) : "memory");
@@ -1174,8 +1179,9 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lanes [32q, 32q+32) =====
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32), column chunks half and half + 2 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     uint32_t acc_seen[2] = {0, 0};
@@ -1193,7 +1199,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (p.save_acts && lane == 0) tma_store_wait_read<0>();  // the previous layer's boxes have been read by their stores
           __syncwarp();
 #pragma unroll 1
-          for (int jj = 0; jj < PF_W / 64; ++jj) {
+          for (int jj = half; jj < PF_W / 64; jj += PF_EPI_WARPS / 4) {
             const uint32_t box = actbuf + jj * (BM * BK * 2) + q * (32 * 128);
             uint32_t packed[32];
 #pragma unroll
@@ -1217,7 +1223,7 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
               mbar_arrive(act_ready(jj));
             }
           }
-        } else {
+        } else if (half == 0) {
           // head: n_valid <= 8 real columns, no activation (model.py:91: softplus follows in the compositing kernel)
           uint32_t v8[8];
           tmem_ld_32x8(t_row, v8);
@@ -1377,7 +1383,7 @@ static int launch_prop_fused(const uint16_t* x, int M, const mip360_layer* trunk
   p.save_acts = acts ? 1 : 0;
   const int tiles = (M + BM - 1) / BM;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  prop_fused_fwd_kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw[0], tw[1], tw[2], tw[3], tw[4], ta[0], ta[1],
+  prop_fused_fwd_kernel<<<grid, PF_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw[0], tw[1], tw[2], tw[3], tw[4], ta[0], ta[1],
                                                                         ta[2], ta[3], p);
   MIP_LAUNCH_CHECK();
   return MIP360_OK;
