@@ -1253,6 +1253,238 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same fused forward for CTA pairs, two row tiles in flight ("ping-pong").  The single-CTA kernel above leaves the
+// tensor pipe idle while a tile's epilogue runs and the epilogue warps idle while its MMAs run (a tile's layers form a
+// chain), and it pulls the full 0.5 MB of weights through L2 for every 128 rows.  Here
+//   * a cluster of two CTAs (tcgen05 cta_group::2, UMMA M = 256) owns 256-row tiles: each CTA keeps its own 128 rows of
+//     activations and stages HALF of every weight chunk (16 KB instead of 32 KB), so weight traffic per row halves;
+//   * every pair works on TWO tiles ("slots"), one accumulator (256 TMEM columns) and one in-place activation buffer
+//     (64 KB) each: the leader issues layer s of slot 0, layer s of slot 1, layer s+1 of slot 0, ... while the epilogue
+//     warps of both CTAs follow one unit behind, so the MMAs of one slot cover the epilogue of the other.
+// Barriers that the MMA issuer waits on live in the leader CTA (the peer's TMA completes on them, the peer's epilogue warps
+// arrive remotely with release.cluster after fence.proxy.async, so their activation stores are visible to the MMA);
+// tcgen05.commit multicasts to both CTAs.  Arithmetic is again that of linear_kernel: bit-identical results.
+// ---------------------------------------------------------------------------------------------
+constexpr int PP_STAGES = 3;  // x 16 KB per CTA
+struct PropPairCfg {
+  static constexpr int X_BYTES = BM * BK * 2;             // 16 KB per slot
+  static constexpr int ACT_BYTES = BM * PF_W * 2;         // 64 KB per slot
+  static constexpr int W_STAGE_BYTES = (PF_W / 2) * BK * 2;  // 16 KB: this CTA's half of a [256 x 64] weight chunk
+  static constexpr int BIAS_BYTES = (PF_TRUNK * PF_W + 64) * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 2 * X_BYTES + 2 * ACT_BYTES + PP_STAGES * W_STAGE_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "pair-fused proposal MLP exceeds shared memory");
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+prop_fused_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w0,
+                           const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                           const __grid_constant__ CUtensorMap tmap_w3, const __grid_constant__ CUtensorMap tmap_wh,
+                           const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                           const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_a3,
+                           const PropFusedParams p) {
+  using Cfg = PropPairCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto xbuf = [&](int P) { return smem_base + (uint32_t)P * Cfg::X_BYTES; };
+  auto actbuf = [&](int P) { return smem_base + 2u * Cfg::X_BYTES + (uint32_t)P * Cfg::ACT_BYTES; };
+  const uint32_t wring = smem_base + 2u * Cfg::X_BYTES + 2u * Cfg::ACT_BYTES;
+  const uint32_t bias_smem = wring + PP_STAGES * Cfg::W_STAGE_BYTES;
+  const uint32_t bar_base = bias_smem + Cfg::BIAS_BYTES;
+  auto w_full = [&](int s) { return bar_base + 8u * s; };
+  auto w_empty = [&](int s) { return bar_base + 8u * (PP_STAGES + s); };
+  auto x_full = [&](int P) { return bar_base + 8u * (2 * PP_STAGES + P); };
+  auto x_empty = [&](int P) { return bar_base + 8u * (2 * PP_STAGES + 2 + P); };
+  auto acc_full = [&](int P) { return bar_base + 8u * (2 * PP_STAGES + 4 + P); };
+  auto epi_done = [&](int P) { return bar_base + 8u * (2 * PP_STAGES + 6 + P); };  // leader's: accumulator drained AND activations written
+  const uint32_t tmem_slot = bar_base + 8u * (2 * PP_STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int unit = blockIdx.x >> 1, nunits = gridDim.x >> 1;
+  const int tiles = (p.M + 2 * BM - 1) / (2 * BM);        // 256-row tiles
+  const int iters = (tiles + 2 * nunits - 1) / (2 * nunits);
+  auto tile_of = [&](int it, int P) { return (it * nunits + unit) * 2 + P; };
+  const CUtensorMap* tmap_w[PF_TRUNK + 1] = {&tmap_w0, &tmap_w1, &tmap_w2, &tmap_w3, &tmap_wh};
+  const CUtensorMap* tmap_a[PF_TRUNK] = {&tmap_a0, &tmap_a1, &tmap_a2, &tmap_a3};
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int P = 0; P < 2; ++P) {
+      mbar_init(x_full(P), 1);
+      mbar_init(x_empty(P), 1);
+      mbar_init(acc_full(P), 1);
+      mbar_init(epi_done(P), 2 * PF_EPI_WARPS);  // both CTAs' epilogue warps
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s <= PF_TRUNK; ++s) prefetch_tmap(tmap_w[s]);
+  }
+  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += PF_THREADS) {
+    const int l = i < PF_TRUNK * PF_W ? i / PF_W : PF_TRUNK;
+    const int c = i - l * PF_W;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(__ldg(p.bias[l] + c)) : "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (one per CTA; completion bytes go to the LEADER's barriers) =====
+      uint32_t ws = 0, wphase = 0, xuses[2] = {0, 0};
+      auto load_x = [&](int it, int P) {
+        const int t = tile_of(it, P);
+        if (it >= iters || t >= tiles) return;
+        mbar_wait(x_empty(P), (xuses[P] & 1u) ^ 1u);
+        ++xuses[P];
+        if (rank == 0) mbar_arrive_expect_tx(x_full(P), 2 * Cfg::X_BYTES);
+        tma_load_2d_pair(xbuf(P), &tmap_x, x_full(P), 0, t * 2 * BM + rank * BM);
+      };
+      load_x(0, 0);
+      load_x(0, 1);
+      for (int it = 0; it < iters; ++it) {
+        for (int s = 0; s <= PF_TRUNK; ++s) {
+          const int kc = s == 0 ? 1 : PF_W / BK;
+          const int rows = s < PF_TRUNK ? PF_W / 2 : 32;    // this CTA's half of the layer's output features
+          for (int P = 0; P < 2; ++P) {
+            if (tile_of(it, P) >= tiles) continue;
+            for (int j = 0; j < kc; ++j) {
+              mbar_wait(w_empty(ws), wphase ^ 1u);
+              if (rank == 0) mbar_arrive_expect_tx(w_full(ws), 2u * rows * BK * 2);
+              tma_load_2d_pair(wring + ws * Cfg::W_STAGE_BYTES, tmap_w[s], w_full(ws), j * BK, rank * rows);
+              if (++ws == PP_STAGES) { ws = 0; wphase ^= 1u; }
+            }
+          }
+          // the next iteration's input rows, a whole iteration ahead (their buffers were released by this iteration's layer 0)
+          if (s == 1) { load_x(it + 1, 0); load_x(it + 1, 1); }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA): M = 256 MMAs over both CTAs' rows =====
+      constexpr uint32_t idesc_trunk = make_idesc_bf16(PF_W, 0, 0, 2 * BM);
+      constexpr uint32_t idesc_head = make_idesc_bf16(64, 0, 0, 2 * BM);
+      uint32_t ws = 0, wphase = 0, units[2] = {0, 0}, xuses[2] = {0, 0};
+      for (int it = 0; it < iters; ++it) {
+        for (int s = 0; s <= PF_TRUNK; ++s) {
+          const int kc = s == 0 ? 1 : PF_W / BK;
+          for (int P = 0; P < 2; ++P) {
+            if (tile_of(it, P) >= tiles) continue;
+            // the slot's previous unit has left the accumulator and (s >= 1) written this layer's input
+            mbar_wait(epi_done(P), (units[P] & 1u) ^ 1u);
+            ++units[P];
+            if (s == 0) { mbar_wait(x_full(P), xuses[P] & 1u); ++xuses[P]; }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)P * PF_W;
+            for (int j = 0; j < kc; ++j) {
+              mbar_wait(w_full(ws), wphase);
+              tc_fence_after();
+              const uint32_t a_addr = s == 0 ? xbuf(P) : actbuf(P) + j * (BM * BK * 2);
+              const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(wring + ws * Cfg::W_STAGE_BYTES, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16<2>(d_tmem, adesc + 2u * k, bdesc + 2u * k, s < PF_TRUNK ? idesc_trunk : idesc_head,
+                             (j | k) != 0 ? 1u : 0u);
+              umma_commit<2>(w_empty(ws));
+              if (++ws == PP_STAGES) { ws = 0; wphase ^= 1u; }
+            }
+            if (s == 0) umma_commit<2>(x_empty(P));
+            umma_commit<2>(acc_full(P));
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): TMEM lanes [32q, 32q+32), column chunks half and half + 2 =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    uint32_t units[2] = {0, 0};
+    for (int it = 0; it < iters; ++it) {
+      const bool both = tile_of(it, 1) < tiles;
+      for (int s = 0; s <= PF_TRUNK; ++s) {
+        for (int P = 0; P < 2; ++P) {
+          if (tile_of(it, P) >= tiles) continue;
+          const int m0 = tile_of(it, P) * 2 * BM + rank * BM;
+          mbar_wait(acc_full(P), units[P] & 1u);
+          ++units[P];
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)P * PF_W;
+          if (s < PF_TRUNK) {
+            const uint32_t bsm = bias_smem + 4u * (s * PF_W);
+            if (p.save_acts && lane == 0) {
+              // this slot's boxes were last read by the stores of its previous unit; the other slot's (one bulk group
+              // younger) may still be in flight
+              if (both) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int jj = half; jj < PF_W / 64; jj += PF_EPI_WARPS / 4) {
+              const uint32_t box = actbuf(P) + jj * (BM * BK * 2) + q * (32 * 128);
+              uint32_t packed[32];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
+                tmem_ld_wait();
+                if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
+                else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                st_shared_v4(box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (p.save_acts && lane == 0) tma_store_2d(tmap_a[s], box, jj * 64, m0 + q * 32);
+            }
+            if (p.save_acts && lane == 0) tma_store_commit();
+          } else if (half == 0) {
+            // head: n_valid <= 8 real columns, no activation (model.py:91: softplus follows in the compositing kernel)
+            const int row = m0 + q * 32 + lane;
+            uint32_t v8[8];
+            tmem_ld_32x8(t_row, v8);
+            tmem_ld_wait();
+            if (row < p.M) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float bv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(bias_smem + 4u * (PF_TRUNK * PF_W + i)));
+                if (i < p.n_valid) p.out[(size_t)row * p.n_valid + i] = __uint_as_float(v8[i]) + bv;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank != 0) mbar_arrive_remote(epi_done(P), 0);
+            else mbar_arrive(epi_done(P));
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync();  // the peer may still signal barriers in this CTA's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
 // ---- host side: tensor maps ------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1381,6 +1613,34 @@ static int launch_prop_fused(const uint16_t* x, int M, const mip360_layer* trunk
   p.M = M;
   p.n_valid = n_valid;
   p.save_acts = acts ? 1 : 0;
+  const int pairs = sm_count() / 2;
+  if (option(OPT_CTA_PAIR) && M >= 2 * BM * 2 * pairs) {
+    // enough 256-row tiles to give every CTA pair two of them: the ping-pong pair kernel
+    static bool configured2[MAX_DEVICES] = {};
+    if (!configured2[dev]) {
+      MIP_CUDA(cudaFuncSetAttribute(prop_fused_pair_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PropPairCfg::SMEM_BYTES));
+      configured2[dev] = true;
+    }
+    for (int l = 0; l < PF_TRUNK; ++l)
+      if ((rc = make_tmap(&tw[l], trunk[l].W, PF_W, trunk[l].k_pad, PF_W / 2)) != MIP360_OK) return rc;
+    if ((rc = make_tmap(&tw[PF_TRUNK], head->W, 64, PF_W, 32)) != MIP360_OK) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(PF_THREADS);
+    cfg.dynamicSmemBytes = PropPairCfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MIP_CUDA(cudaLaunchKernelEx(&cfg, prop_fused_pair_fwd_kernel, tx, tw[0], tw[1], tw[2], tw[3], tw[4], ta[0], ta[1], ta[2],
+                                ta[3], p));
+    MIP_LAUNCH_CHECK();
+    return MIP360_OK;
+  }
   const int tiles = (M + BM - 1) / BM;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   prop_fused_fwd_kernel<<<grid, PF_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw[0], tw[1], tw[2], tw[3], tw[4], ta[0], ta[1],
