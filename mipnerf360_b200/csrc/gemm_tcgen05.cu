@@ -1033,7 +1033,7 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
 //               activations are needed for the backward pass, a TMA store of the same 4 KB box to HBM).  A tile costs
 //               52 N=256 MMAs (~4.5 us) but four 128 x 256 epilogues, which four warps need ~10 us for (each waits out
 //               its own tcgen05.ld latencies): the kernel is epilogue-bound, so every TMEM lane quarter is served by
-//               TWO warps, one per pair of 64-column chunks
+//               FOUR warps, one per 64-column chunk
 // Pipelining inside a tile: layer s+1's k-chunk j only needs output columns [64j, 64j+64) of layer s, so its MMAs start
 // as soon as the epilogue has written that chunk (per-chunk mbarriers); layers alternate between two TMEM accumulators
 // and two activation buffers.  Arithmetic (MMA order, epilogue) is that of linear_kernel: results are bit-identical to
@@ -1042,7 +1042,7 @@ head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w4, const
 constexpr int PF_W = 256;        // trunk width
 constexpr int PF_TRUNK = 4;      // trunk layers
 constexpr int PF_STAGES = 4;     // weight ring: 128 KB in flight hide the L2 latency of the 32 KB chunks
-constexpr int PF_EPI_WARPS = 8;  // two per TMEM lane quarter
+constexpr int PF_EPI_WARPS = 16; // four per TMEM lane quarter, one per 64-column chunk
 constexpr int PF_THREADS = 64 + 32 * PF_EPI_WARPS;
 struct PropFusedCfg {
   static constexpr int X_BYTES = BM * BK * 2;                    // 16 KB (K0 = 64)
@@ -1201,18 +1201,17 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll 1
           for (int jj = half; jj < PF_W / 64; jj += PF_EPI_WARPS / 4) {
             const uint32_t box = actbuf + jj * (BM * BK * 2) + q * (32 * 128);
-            uint32_t packed[32];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              uint32_t v[32];
+              uint32_t v[32], packed[16];
               tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
               tmem_ld_wait();
-              if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
-              else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
-            }
+              if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, packed);
+              else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, packed);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              st_shared_v4(box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+              for (int c = 0; c < 4; ++c)
+                st_shared_v4(box + row_off + (((4 * h + c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -1262,6 +1261,12 @@ prop_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 //   * every pair works on TWO tiles ("slots"), one accumulator (256 TMEM columns) and one in-place activation buffer
 //     (64 KB) each: the leader issues layer s of slot 0, layer s of slot 1, layer s+1 of slot 0, ... while the epilogue
 //     warps of both CTAs follow one unit behind, so the MMAs of one slot cover the epilogue of the other.
+// What bounds it: reading a 128 x 256 fp32 accumulator out of tensor memory (128 KB at 64 B/clk/SM) takes as long as the 16
+// MMAs that produce it (K = 256), and a slot's MMA -> epilogue -> next layer's MMA chain is serial, so with two slots the
+// tensor pipe reaches ~50 % (ncu).  Splitting a layer into two N = 128 column halves so that the first half is read while
+// the second accumulates was built and measured slower (0.59 vs 0.46 ms per 1M rows): M = 128-per-CTA x N = 128 MMAs need
+// 128 B/clk of shared-memory operand bandwidth, all there is.  Inference launches four epilogue warps per TMEM lane
+// quarter, training (activations saved with TMA stores) two.
 // Barriers that the MMA issuer waits on live in the leader CTA (the peer's TMA completes on them, the peer's epilogue warps
 // arrive remotely with release.cluster after fence.proxy.async, so their activation stores are visible to the MMA);
 // tcgen05.commit multicasts to both CTAs.  Arithmetic is again that of linear_kernel: bit-identical results.
@@ -1301,6 +1306,7 @@ prop_fused_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
   const uint32_t tmem_slot = bar_base + 8u * (2 * PP_STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nepi = (int)(blockDim.x >> 5) - 2;   // epilogue warps: 8 or 16
   const int rank = (int)cluster_ctarank();
   const int unit = blockIdx.x >> 1, nunits = gridDim.x >> 1;
   const int tiles = (p.M + 2 * BM - 1) / (2 * BM);        // 256-row tiles
@@ -1315,13 +1321,13 @@ prop_fused_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
       mbar_init(x_full(P), 1);
       mbar_init(x_empty(P), 1);
       mbar_init(acc_full(P), 1);
-      mbar_init(epi_done(P), 2 * PF_EPI_WARPS);  // both CTAs' epilogue warps
+      mbar_init(epi_done(P), 2 * nepi);  // both CTAs' epilogue warps
     }
     fence_barrier_init();
     prefetch_tmap(&tmap_x);
     for (int s = 0; s <= PF_TRUNK; ++s) prefetch_tmap(tmap_w[s]);
   }
-  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += PF_THREADS) {
+  for (int i = threadIdx.x; i < PF_TRUNK * PF_W + 64; i += blockDim.x) {
     const int l = i < PF_TRUNK * PF_W ? i / PF_W : PF_TRUNK;
     const int c = i - l * PF_W;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(__ldg(p.bias[l] + c)) : "memory");
@@ -1424,32 +1430,33 @@ prop_fused_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const __g
           const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)P * PF_W;
           if (s < PF_TRUNK) {
             const uint32_t bsm = bias_smem + 4u * (s * PF_W);
-            if (p.save_acts && lane == 0) {
-              // this slot's boxes were last read by the stores of its previous unit; the other slot's (one bulk group
-              // younger) may still be in flight
-              if (both) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            if (p.save_acts) {
+              // this slot's boxes were last read by the stores of its previous unit; the bulk group of the other slot's
+              // unit in between (one group younger) may still be in flight
+              if (lane == 0) {
+                if (both) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              }
+              __syncwarp();
             }
-            __syncwarp();
 #pragma unroll 1
-            for (int jj = half; jj < PF_W / 64; jj += PF_EPI_WARPS / 4) {
+            for (int jj = half; jj < PF_W / 64; jj += nepi / 4) {
               const uint32_t box = actbuf(P) + jj * (BM * BK * 2) + q * (32 * 128);
-              uint32_t packed[32];
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                uint32_t v[32];
+                uint32_t v[32], packed[16];
                 tmem_ld_32x32(t_row + jj * 64 + h * 32, v);
                 tmem_ld_wait();
-                if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
-                else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, &packed[16 * h]);
-              }
+                if (p.act[s] == ACT_RELU) fwd_relu_packed(v, bsm + (jj * 64 + h * 32) * 4u, packed);
+                else fwd_sigmoid_fast_packed(v, bsm + (jj * 64 + h * 32) * 4u, packed);
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                st_shared_v4(box + row_off + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                for (int c = 0; c < 4; ++c)
+                  st_shared_v4(box + row_off + (((4 * h + c) ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+              }
               fence_proxy_async_smem();
               __syncwarp();
               if (p.save_acts && lane == 0) tma_store_2d(tmap_a[s], box, jj * 64, m0 + q * 32);
             }
-            if (p.save_acts && lane == 0) tma_store_commit();
+            if (p.save_acts && lane == 0) tma_store_commit();   // one bulk group per unit
           } else if (half == 0) {
             // head: n_valid <= 8 real columns, no activation (model.py:91: softplus follows in the compositing kernel)
             const int row = m0 + q * 32 + lane;
@@ -1626,7 +1633,10 @@ static int launch_prop_fused(const uint16_t* x, int M, const mip360_layer* trunk
     if ((rc = make_tmap(&tw[PF_TRUNK], head->W, 64, PF_W, 32)) != MIP360_OK) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(PF_THREADS);
+    // Same-box A/B (1M rows): inference 0.45 ms with four epilogue warps per TMEM lane quarter against 0.48 with two;
+    // training (activations saved by TMA stores, whose issue slots then matter less than their queueing) 0.58 ms with two
+    // against 0.66 with four, and 0.66-0.68 ms with plain 16-byte stores from a row-major read-back of the boxes.
+    cfg.blockDim = dim3(64 + 32 * (acts ? 8 : 16));
     cfg.dynamicSmemBytes = PropPairCfg::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
