@@ -327,6 +327,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     prefetch_tmap(&tmap_out);
     if (EPI == EPI_DGRAD) prefetch_tmap(&tmap_y);
   }
+  __syncthreads();  // orders the barrier initialisation before tcgen05.alloc's write of the TMEM address (once per kernel)
   if (warp == 1) {
     tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish<CG>();

@@ -76,17 +76,18 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics
-// (.release.cta): what the arrival publishes is this CTA's tensor-memory reads (tcgen05.fence::before_thread_sync) and
-// its own shared memory, already made visible to the async proxy by fence.proxy.async — an explicit .release.cluster
-// compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR and waits for every outstanding global store of the warp (ncu: 20 % of
-// the samples of the pair-fused proposal kernel sat there).
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Cluster scope, RELAXED: what
+// the arrival publishes is this CTA's tensor-memory reads (ordered by tcgen05.fence::before_thread_sync) and its own
+// shared memory as seen by the async proxy (ordered by fence.proxy.async) — no generic-proxy data crosses CTAs.
+// .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR and waits for every outstanding global store of
+// the warp (ncu: 20 % of the samples of the pair-fused proposal kernel sat there; the fused-head GEMM, whose epilogue
+// has red.global stores in flight, lost 4 % to it).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(bar),
       "r"(cta)
       : "memory");

@@ -748,7 +748,9 @@ def test_layer_fused_proposal_mlp_is_bit_identical_to_the_layer_by_layer_path():
                 p.uniform_(-0.5, 0.5)  # non-trivial biases
     pk = net._packed
     assert pk.narrow_shape()
-    for M in (128, 1000, 128 * 148 + 77, 300000):
+    # < 37 888 rows: the single-CTA kernel; from there on CTA pairs with two 256-row tiles in flight (37 888 = every pair gets
+    # exactly two tiles; + 129: one more tile whose second CTA holds a single valid row; 262 144 = a 4 096-ray render chunk)
+    for M in (128, 1000, 128 * 148 + 77, 37888, 37888 + 129, 262144, 300000):
         x = (torch.randn(M, 64, device=dev) * 0.7).bfloat16()
         x[:, 58:] = 0
         res = {}
