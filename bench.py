@@ -281,7 +281,9 @@ def bench_render(model, dev, world, barrier, pk, chunk_sizes, cases):
     flop_per_ray = N_SAMPLES * (PROP_FLOP_PER_SAMPLE + NERF_FLOP_PER_SAMPLE)
     for case in cases:
         h, w = case["height"], case["width"]
-        for chunks in chunk_sizes:
+        # 128 = the reference CLI's default chunk (config.py:49): launch-latency territory, only on frames of <= 1 M rays
+        sizes = list(chunk_sizes) + ([128] if h * w <= (1 << 20) and 128 not in chunk_sizes else [])
+        for chunks in sizes:
             warm_h = max(3, min(h, (8 * chunks * world + w - 1) // w))  # a few chunks per rank
             render_frame(model, case["c2w"], warm_h, w, case["focal"], case["near"], case["far"], case["ndc"], chunks)
             barrier()
