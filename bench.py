@@ -434,12 +434,19 @@ def main():
     ms_step_instrumented = p0.elapsed_time(p1) / args.steps
 
     # end to end through the public API: pinned host rays/pixels in, losses out, every step
+    # Every step copies its batch from pinned host memory and its three losses are read back on the host; the read of step
+    # i is taken after step i+1 has been enqueued (step_host(wait=False)), so the GPU does not idle across the read-back.
     for _ in range(2):
         trainer.step_host(rays_h, pixels_h)
     barrier()
     t0 = time.perf_counter()
+    pending, losses_seen = None, 0
     for _ in range(args.steps):
-        trainer.step_host(rays_h, pixels_h)
+        h = trainer.step_host(rays_h, pixels_h, wait=False)
+        if pending is not None:
+            losses_seen += int(bool(torch.isfinite(pending.result()).all()))
+        pending = h
+    losses_seen += int(bool(torch.isfinite(pending.result()).all()))
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
@@ -491,7 +498,8 @@ def main():
             "config": workload_config(world, args.rays, args.scaling),
             "clocks": clk,
             "e2e": {"value": total_rays / float(e2e_s), "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 12},
+                    "d2h_bytes_per_step": 12, "losses_read": losses_seen,
+                    "readback": "every step's losses are read on the host, the read of step i after step i+1 was enqueued"},
             "gpu_launches": launches,
             "launch_mode": "eager" if args.no_graph else "one CUDA graph per iteration (kernels counted at capture)",
             "roofline": roof,

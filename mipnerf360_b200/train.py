@@ -197,6 +197,7 @@ class Trainer:
         self.graph_warmup = int(graph_warmup)
         self._graphs = {}       # batch size -> dict(graph, rays, pixels, out, launches)
         self.replayed_launches = 0  # kernels of this library launched through graph replays (the C-side counter only sees captures)
+        self._host_out, self._host_ev, self._host_i = None, None, 0   # step_host: pinned result slots
         self._eager_calls = 0
         self._hyper = None      # device [3 sub-steps, 3] = lr, 1 - beta1^t, sqrt(1 - beta2^t), read by the captured AdamW
         self._capture_substep = None
@@ -422,8 +423,11 @@ class Trainer:
             return self._step_graph(rays, pixels)
         return self._step_eager(rays, pixels)
 
-    def step_host(self, rays_host, pixels_host):
-        """Same, from pinned host buffers: H2D copy of the batch, the iteration, D2H read of the losses."""
+    def step_host(self, rays_host, pixels_host, wait=True):
+        """Same, from pinned host buffers: H2D copy of the batch, the iteration, D2H read of the losses
+        [loss_prop, loss_all, psnr].  wait=False returns a handle whose .result() blocks for this step's losses: a loop
+        that enqueues step i+1 before asking for step i's result keeps the GPU busy across the read-back (the copies and
+        the replay of i+1 are queued behind step i on the same stream)."""
         dev = next(self.model.parameters()).device
         if self.use_graph and int(pixels_host.shape[0]) in self._graphs and _lib.PROFILE is None:
             lp, la, psnr = self.step(rays_host, pixels_host)  # straight into the graph's static input buffers
@@ -431,7 +435,25 @@ class Trainer:
             rays = Rays(*[r.to(dev, non_blocking=True) for r in rays_host])
             pixels = pixels_host.to(dev, non_blocking=True)
             lp, la, psnr = self.step(rays, pixels)
-        return torch.stack([lp, la, psnr]).cpu()
+        if self._host_out is None:
+            self._host_out = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._host_ev = [torch.cuda.Event() for _ in range(2)]
+        i = self._host_i = (self._host_i + 1) % 2   # two slots: the previous step's result may not have been read yet
+        self._host_out[i].copy_(torch.stack([lp, la, psnr]), non_blocking=True)
+        self._host_ev[i].record()
+        h = HostResult(self._host_out[i], self._host_ev[i])
+        return h.result() if wait else h
+
+
+class HostResult:
+    """Losses of one Trainer.step_host(wait=False) call on their way to pinned host memory."""
+
+    def __init__(self, buf, event):
+        self._buf, self._event = buf, event
+
+    def result(self):
+        self._event.synchronize()
+        return self._buf.clone()
 
 
 def check_sharded_equals_unsharded(device, rays_per_rank=512, num_samples=64, hidden_proposal=256, hidden_nerf=1024,

@@ -442,6 +442,21 @@ def test_trainer_cuda_graph_matches_eager():
     out = graphed.step_host(rays_h, pix_h)
     ref = eager.step_host(rays_h, pix_h)
     torch.testing.assert_close(out, ref, rtol=5e-3, atol=5e-3)
+    # pipelined read-back: step i's losses are asked for after step i+1 has been enqueued; each handle returns its own
+    # step's values (two pinned slots), equal to the blocking calls of the eager trainer on the same batches
+    host_batches = [generic_rays(256, 400 + i, pin=True) for i in range(4)]
+    want = [eager.step_host(r, p) for r, p in host_batches]
+    got, pending = [], None
+    for r, p in host_batches:
+        h = graphed.step_host(r, p, wait=False)
+        if pending is not None:
+            got.append(pending.result())
+        pending = h
+    got.append(pending.result())
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a.device.type == "cpu" and a.shape == (3,)
+        torch.testing.assert_close(a, b, rtol=5e-3, atol=5e-3, msg=lambda s: f"pipelined step {i}: {s}")
+    assert not all(torch.equal(got[0], g) for g in got[1:])   # different batches, different losses: no slot was overwritten
     rays2, pix2 = generic_rays(128, 301, device=dev)
     graphed.step(rays2, pix2)
     graphed.step(rays2, pix2)
