@@ -166,6 +166,8 @@ def kernel_work(name, a):
         return "tensor", 2.0 * a[0] * a[1] * a[2]
     if name == "mip360_linear_fwd_head":  # M, N, K, act : trunk layer + the 4 head columns in its epilogue
         return "tensor", 2.0 * a[0] * a[1] * a[2] + 2.0 * a[0] * a[1] * 4
+    if name == "mip360_mlp_fwd_fused_narrow":  # M, layers, n_valid (, 1 = activations saved): the whole proposal MLP
+        return "tensor", float(a[0]) * PROP_FLOP_PER_SAMPLE
     if name == "mip360_head_bwd":         # M, N, act, ldw : trunk output read, its gradient written, 16 B/row of g
         return "hbm", a[0] * (4.0 * a[1] + 16)
     if name == "mip360_linear_dgrad":     # M, N, K, act
