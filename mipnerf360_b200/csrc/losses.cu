@@ -233,25 +233,47 @@ interlevel_kernel(const float* __restrict__ w_hat, const float* __restrict__ b_p
   float g_scale = 0.f;
   if (BWD) g_scale = *g_loss_ptr / batch_div;
   if ((N & 3) == 0 && bound_mode == 0) {
-    // four consecutive columns per thread: 16-byte loads / stores, the column index by a 32-bit modulo per quad
+    // four consecutive columns per thread (16-byte loads / stores), U quads in flight per thread, the batch bounds as
+    // floats in shared memory, the quad's column carried along instead of a 64-bit modulo per quad.
+    __shared__ float bnd_s[MIP360_MAX_SAMPLES];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bnd_s[i] = (float)bound_total[i];
+    __syncthreads();
+    constexpr int U = 4;
     const long long quads = total >> 2, qstride = (long long)gridDim.x * blockDim.x;
-    const int nq = N >> 2;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += qstride) {
-      const int i0 = (int)(q % nq) << 2;
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_hat) + q);
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
-      float go[4];
-      float part = 0.f;
+    const int nq = N >> 2, qstep = (int)(qstride % nq);
+    long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c0 = (int)(q0 % nq);
+    for (; q0 < quads; q0 += U * qstride) {
+      float4 w4[U];
+      int col[U];
+      int c = c0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float bnd = (float)bound_total[i0 + k];
-        const float r = fmaxf(bnd - w[k], 0.f);
-        const float den = w[k] + 1e-6f;
-        if (!BWD) acc += (double)((r * r) / den);
-        else go[k] = g_scale * (-2.f * r / den - (r * r) / (den * den));
+      for (int u = 0; u < U; ++u) {
+        const long long q = q0 + u * qstride;
+        col[u] = c;
+        c = c + qstep >= nq ? c + qstep - nq : c + qstep;
+        if (q < quads) w4[u] = __ldg(reinterpret_cast<const float4*>(w_hat) + q);
       }
-      (void)part;
-      if (BWD) reinterpret_cast<float4*>(g_w_hat)[q] = make_float4(go[0], go[1], go[2], go[3]);
+      c0 = c;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long q = q0 + u * qstride;
+        if (q >= quads) break;
+        const float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+        const float4 b4 = *reinterpret_cast<const float4*>(&bnd_s[col[u] << 2]);
+        const float bnd[4] = {b4.x, b4.y, b4.z, b4.w};
+        float go[4], term[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float r = fmaxf(bnd[k] - w[k], 0.f);
+          const float den = w[k] + 1e-6f;
+          if (!BWD) term[k] = (r * r) / den;
+          else go[k] = g_scale * (-2.f * r / den - (r * r) / (den * den));
+        }
+        // the four non-negative terms of a quad are summed in fp32 (pairwise), quads in fp64
+        if (!BWD) acc += (double)((term[0] + term[1]) + (term[2] + term[3]));
+        if (BWD) reinterpret_cast<float4*>(g_w_hat)[q] = make_float4(go[0], go[1], go[2], go[3]);
+      }
     }
     if (!BWD) block_sum_to_partial<256>(acc, partials);
     return;
