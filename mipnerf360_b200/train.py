@@ -359,9 +359,21 @@ class Trainer:
         if not all(g["fused"] for g in self.opt.groups.values()):
             raise RuntimeError("graph=True needs the fused AdamW path (one PackedMLP per net)")
         dev = pixels.device
-        if self._hyper is None:
-            self._hyper = torch.zeros((3, 3), device=dev, dtype=torch.float32)
-        st = dict(rays=Rays(*[r.detach().clone() for r in rays]), pixels=pixels.detach().clone(), graph=torch.cuda.CUDAGraph())
+        # static inputs of the captured iteration: the ray fields, the pixels and the three sub-steps' optimiser scalars
+        # are views of ONE flat buffer (each 64-byte aligned), so that a host batch arrives with a single copy
+        fields = [r.detach() for r in rays] + [pixels.detach()]
+        assert all(f.dtype == torch.float32 for f in fields)
+        offs, off = [], 0
+        for f in fields:
+            offs.append(off)
+            off += (f.numel() + 15) // 16 * 16
+        flat = torch.zeros(off + 16, device=dev, dtype=torch.float32)
+        views = [flat[o:o + f.numel()].view(f.shape) for o, f in zip(offs, fields)]
+        for v, f in zip(views, fields):
+            v.copy_(f)
+        st = dict(rays=Rays(*views[:-1]), pixels=views[-1], hyper=flat[off:off + 9].view(3, 3), flat=flat, offs=offs,
+                  host=None, graph=torch.cuda.CUDAGraph())
+        self._hyper = st["hyper"]   # read by _optim while capturing: the AdamW launches take lr / bias corrections from here
         # host-side counters advance while capturing (no kernel runs); they are restored and advanced per replay instead
         saved = (self.sched_step, self.opt.groups["prop"]["step"], self.opt.groups["nerf"]["step"], dict(self._grads_clean))
         self._capture_substep = 0
@@ -382,7 +394,7 @@ class Trainer:
             self._grads_clean = clean_after
         return st
 
-    def _step_graph(self, rays, pixels):
+    def _step_graph(self, rays, pixels, raw=False):
         key = int(pixels.shape[0])
         st = self._graphs.get(key)
         if st is None:
@@ -404,15 +416,35 @@ class Trainer:
                 self._grads_clean = {"prop": True, "nerf": True}
                 torch.cuda.synchronize()
                 return self._step_eager(rays, pixels)
-        for dst, src in zip(st["rays"], rays):
-            dst.copy_(src, non_blocking=True)
-        st["pixels"].copy_(pixels, non_blocking=True)
-        self._hyper.copy_(self._hyper_rows())  # 36 bytes, staged copy from pageable memory
+        fields = list(rays) + [pixels]
+        if all(f.device.type == "cpu" for f in fields):
+            # host batch: packed on the CPU into a pinned image of the flat buffer (two of them: the previous step's copy may
+            # still be in flight), optimiser scalars included, then ONE host->device copy
+            if st["host"] is None:
+                st["host"] = [torch.zeros(st["flat"].numel(), dtype=torch.float32).pin_memory() for _ in range(2)]
+                st["host_ev"] = [torch.cuda.Event() for _ in range(2)]
+                st["host_i"] = 0
+            i = st["host_i"] = 1 - st["host_i"]
+            st["host_ev"][i].synchronize()      # the copy that last read this image has completed
+            hbuf = st["host"][i]
+            for o, f in zip(st["offs"], fields):
+                hbuf[o:o + f.numel()].copy_(f.reshape(-1))
+            n = st["flat"].numel() - 16
+            hbuf[n:n + 9].copy_(self._hyper_rows().reshape(-1))
+            st["flat"].copy_(hbuf, non_blocking=True)
+            st["host_ev"][i].record()
+        else:
+            for dst, src in zip(st["rays"], rays):
+                dst.copy_(src, non_blocking=True)
+            st["pixels"].copy_(pixels, non_blocking=True)
+            st["hyper"].copy_(self._hyper_rows())  # 36 bytes, staged copy from pageable memory
         st["graph"].replay()
         self.replayed_launches += st["launches"]
         self.sched_step += 3
         self.opt.groups["prop"]["step"] += 2
         self.opt.groups["nerf"]["step"] += 1
+        if raw:
+            return st["out"]   # the graph's static result tensor: valid until the next replay (stream-ordered reads only)
         out = st["out"].clone()
         return out[0], out[1], out[2]
 
@@ -430,16 +462,16 @@ class Trainer:
         the replay of i+1 are queued behind step i on the same stream)."""
         dev = next(self.model.parameters()).device
         if self.use_graph and int(pixels_host.shape[0]) in self._graphs and _lib.PROFILE is None:
-            lp, la, psnr = self.step(rays_host, pixels_host)  # straight into the graph's static input buffers
+            out = self._step_graph(rays_host, pixels_host, raw=True)  # one copy into the graph's static input buffer
         else:
             rays = Rays(*[r.to(dev, non_blocking=True) for r in rays_host])
             pixels = pixels_host.to(dev, non_blocking=True)
-            lp, la, psnr = self.step(rays, pixels)
+            out = torch.stack(self.step(rays, pixels))
         if self._host_out is None:
             self._host_out = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
             self._host_ev = [torch.cuda.Event() for _ in range(2)]
         i = self._host_i = (self._host_i + 1) % 2   # two slots: the previous step's result may not have been read yet
-        self._host_out[i].copy_(torch.stack([lp, la, psnr]), non_blocking=True)
+        self._host_out[i].copy_(out, non_blocking=True)
         self._host_ev[i].record()
         h = HostResult(self._host_out[i], self._host_ev[i])
         return h.result() if wait else h
