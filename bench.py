@@ -422,18 +422,6 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
     clk = clocks.stop(t_begin, t_end) if clocks else None
-    # the same K steps again with every kernel launch bracketed by CUDA events (per-kernel durations for the
-    # roofline; ~300 extra event records per step and one C call per GEMM instead of one per MLP, so this pass
-    # is kept out of `value`)
-    _lib.PROFILE = []
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(args.steps):
-        trainer.step(rays, pixels)
-    p1.record()
-    barrier()
-    prof, _lib.PROFILE = _lib.PROFILE, None
-    ms_step_instrumented = p0.elapsed_time(p1) / args.steps
 
     # end to end through the public API: pinned host rays/pixels in, losses out, every step
     # Every step copies its batch from pinned host memory and its three losses are read back on the host; the read of step
@@ -448,12 +436,26 @@ def main():
         if pending is not None:
             losses_seen += int(bool(torch.isfinite(pending.result()).all()))
         pending = h
-    losses_seen += int(bool(torch.isfinite(pending.result()).all()))
+    losses_seen += int(bool(torch.isfinite(pending.result()).all()))  # the last step's losses are on the host: the job is done
+    e2e_wall = time.perf_counter() - t0
     barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    e2e_s = torch.tensor([e2e_wall / args.steps], device=dev, dtype=torch.float64)  # max over ranks below
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     h2d = sum(r.numel() * 4 for r in rays_h) + pixels_h.numel() * 4
+
+    # the same K steps again with every kernel launch bracketed by CUDA events (per-kernel durations for the
+    # roofline; ~300 extra event records per step and one C call per GEMM instead of one per MLP, so this pass
+    # is kept out of `value`)
+    _lib.PROFILE = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        trainer.step(rays, pixels)
+    p1.record()
+    barrier()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    ms_step_instrumented = p0.elapsed_time(p1) / args.steps
 
     # N > 1: the weak-scaling figure (every rank a full 16384-ray batch) next to the strong-scaling headline
     weak = None
