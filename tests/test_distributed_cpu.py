@@ -99,3 +99,36 @@ def test_lr_schedule_matches_reference_formula():
         ref = delay * np.exp(np.log(cfg["lr_init"]) * (1 - t) + np.log(cfg["lr_final"]) * t)
         assert math.isclose(lr_at(step, **cfg), ref, rel_tol=1e-12)
     assert lr_at(5, 1e-3, 1e-4, 10) == pytest.approx(1e-3 * (0.1 ** 0.5))
+
+
+def test_constant_sampling_vectors_are_the_reference_formulas_and_cached():
+    """ops.pdf_u_base / the level-0 s grid (ray.py:31-38,100): same torch ops as the reference, built once per device."""
+    import torch
+    from mipnerf360_b200 import ops
+    eps = float(torch.finfo(torch.float32).eps)
+    for m in (33, 65, 129):
+        u = ops.pdf_u_base(m, True, "cpu")
+        assert torch.equal(u, torch.arange(m) * (1 / m))                       # ray.py:31-33 before the jitter
+        assert ops.pdf_u_base(m, True, torch.device("cpu")) is u               # cached
+        d = ops.pdf_u_base(m, False, "cpu")
+        assert torch.equal(d, torch.linspace(0.0, 1.0 - eps, m))               # ray.py:38
+        assert d is not u and ops.pdf_u_base(m, False, "cpu") is d
+    assert ops.jitter_scale(65) == float(torch.tensor(1 / 65 - eps, dtype=torch.float32))
+
+
+def test_host_result_returns_a_private_copy():
+    """train.HostResult (Trainer.step_host(wait=False)): result() hands out a copy, the pinned slot may be reused."""
+    import torch
+    from mipnerf360_b200.train import HostResult
+
+    class _Ev:
+        waited = 0
+
+        def synchronize(self):
+            self.waited += 1
+
+    buf, ev = torch.tensor([1.0, 2.0, 3.0]), _Ev()
+    h = HostResult(buf, ev)
+    out = h.result()
+    buf.zero_()
+    assert ev.waited == 1 and out.tolist() == [1.0, 2.0, 3.0]
